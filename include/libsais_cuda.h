@@ -1,0 +1,78 @@
+/*
+ * libsais_cuda.h -- extras of the B200 implementation that the reference interface has no
+ * counterpart for: explicit GPU selection, device-pointer entry points (so a benchmark can
+ * time device work with CUDA events, SURVEY.md §8b "extras needed by the metric"), and the
+ * per-kernel-class / per-round statistics the roofline report is built from.
+ *
+ * The drop-in boundary itself is include/libsais.h and include/libsais64.h.
+ */
+#ifndef LIBSAIS_CUDA_H
+#define LIBSAIS_CUDA_H 1
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIBSAIS_CUDA_MAX_KERNEL_CLASSES 32
+
+typedef struct libsais_cuda_stats {
+    int32_t  n_classes;                                   /* valid entries below */
+    int32_t  n_rounds;                                    /* prefix-doubling rounds of the last SA build (incl. round 0) */
+    uint64_t total_launches;                              /* kernels launched by the last call */
+    uint64_t launches[LIBSAIS_CUDA_MAX_KERNEL_CLASSES];   /* per kernel class */
+    double   ms[LIBSAIS_CUDA_MAX_KERNEL_CLASSES];         /* device time per class (profiling on), CUDA events */
+    double   bytes[LIBSAIS_CUDA_MAX_KERNEL_CLASSES];      /* ALGORITHMIC bytes per class */
+    double   device_ms;                                   /* first kernel -> last kernel of the last call */
+    uint64_t workspace_bytes;                             /* current device workspace */
+} libsais_cuda_stats;
+
+typedef struct libsais_cuda_round {
+    uint64_t h;          /* symbols already sorted when the round started (0 = initial k-mer sort) */
+    uint64_t n_active;   /* suffixes sorted in the round */
+    uint64_t n_groups;   /* unresolved groups left after the round */
+    int32_t  passes;     /* radix digit passes */
+    int32_t  key_bits;   /* key bits sorted */
+} libsais_cuda_round;
+
+/* Number of CUDA devices visible (0 when there is no usable GPU). */
+int32_t libsais_cuda_device_count(void);
+
+/* Context bound to GPU `device` (-1: $LIBSAIS_CUDA_DEVICE, else the calling thread's current
+ * device).  Same object type as libsais_create_ctx(); free with libsais_free_ctx(). */
+void *  libsais_cuda_create_ctx(int32_t device);
+
+/* The cudaStream_t all work of this context is issued on. */
+void *  libsais_cuda_stream(const void * ctx);
+
+/* Record a CUDA-event pair around every kernel launch (per-class device times in the stats). */
+int32_t libsais_cuda_set_profiling(const void * ctx, int32_t on);
+
+/* Statistics of the last call made with this context (ctx == NULL: calling thread's default). */
+int32_t libsais_cuda_get_stats(const void * ctx, libsais_cuda_stats * out);
+int32_t libsais_cuda_get_round(const void * ctx, int32_t round, libsais_cuda_round * out);
+const char * libsais_cuda_kernel_class_name(int32_t kernel_class);
+/* cudaError_t of the last failure seen by the context (0 = none). */
+int32_t libsais_cuda_last_error(const void * ctx);
+
+/* ---- device-pointer entry points: every pointer is DEVICE memory on the context's GPU, the
+ * call returns after the work completed on the context's stream.  n < 2^32 - 16.
+ * Same results as the host functions they mirror.  Return 0 (bwt: primary index) / -1 / -2. */
+
+/* SA[0..n) (uint32 slots) of T; mirrors libsais() [reference include/libsais.h:84]. */
+int64_t libsais_cuda_sa_dev(const void * ctx, const uint8_t * d_T, uint32_t * d_SA, int64_t n);
+/* BWT of T into d_U (must not alias d_T) and the primary index; mirrors libsais_bwt() [:182]. */
+int64_t libsais_cuda_bwt_dev(const void * ctx, const uint8_t * d_T, uint8_t * d_U, int64_t n);
+/* PLCP from T and SA; mirrors libsais_plcp() [:368]. */
+int64_t libsais_cuda_plcp_dev(const void * ctx, const uint8_t * d_T, const uint32_t * d_SA, uint32_t * d_PLCP, int64_t n);
+/* LCP from PLCP and SA (d_LCP must not alias); mirrors libsais_lcp() [:398]. */
+int64_t libsais_cuda_lcp_dev(const void * ctx, const uint32_t * d_PLCP, const uint32_t * d_SA, uint32_t * d_LCP, int64_t n);
+/* Inverse BWT; mirrors libsais_unbwt() [:289]. */
+int64_t libsais_cuda_unbwt_dev(const void * ctx, const uint8_t * d_B, uint8_t * d_U, int64_t n, int64_t primary);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LIBSAIS_CUDA_H */

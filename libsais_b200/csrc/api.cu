@@ -1,0 +1,501 @@
+// api.cu -- the C-ABI of libsais_cuda: every symbol of include/libsais.h and include/libsais64.h
+// (host pointers; the drop-in boundary, reference src/libsais.c:7008-7322, :8020-8112,
+// :8363-8517 and src/libsais64.c:7058-7250, :8034-8400) plus the device-pointer extras of
+// include/libsais_cuda.h.  Argument validation, n <= 1 fast paths and return codes mirror the
+// reference; all computing is done by the CUDA pipelines -- there is no CPU
+// fallback: without a usable GPU every computing call returns -2.
+#include "core.h"
+#include <cstring>
+#include <cstdlib>
+#include <new>
+
+#define LIBSAIS_OPENMP 1      /* export the *_omp symbols unconditionally */
+#include "../../include/libsais.h"
+#include "../../include/libsais64.h"
+#include "../../include/libsais_cuda.h"
+
+using namespace lsc;
+
+namespace {
+
+Ctx *new_ctx(int device)
+{
+    if (device < 0) {
+        const char *env = getenv("LIBSAIS_CUDA_DEVICE");
+        if (env && *env) device = atoi(env);
+        else if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    int prev = -1; cudaGetDevice(&prev);
+    Ctx *c = new (std::nothrow) Ctx();
+    if (!c) return nullptr;
+    bool ok = c->init(device);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (!ok) { c->destroy(); delete c; return nullptr; }
+    return c;
+}
+
+struct DefaultCtx {
+    Ctx *c = nullptr;
+    ~DefaultCtx() { if (c) { c->destroy(); delete c; c = nullptr; } }
+};
+thread_local DefaultCtx tl_default;
+
+Ctx *default_ctx()
+{
+    if (!tl_default.c) tl_default.c = new_ctx(-1);
+    return tl_default.c;
+}
+
+Ctx *as_ctx(const void *p) { return const_cast<Ctx *>(static_cast<const Ctx *>(p)); }
+
+// RAII bracket of one API call on a context: device guard, fresh stats/arena, device timing.
+struct Call {
+    Ctx &c; DeviceGuard g; cudaEvent_t e0 = nullptr, e1 = nullptr; bool timed = false;
+    explicit Call(Ctx &ctx) : c(ctx), g(ctx.device) { c.reset_stats(); c.reset_arena(); }
+    void start_timer() {
+        if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) { cudaEventRecord(e0, c.stream); timed = true; }
+    }
+    void stop_timer() { if (timed) cudaEventRecord(e1, c.stream); }
+    // sync, fold timings; returns false on any CUDA failure
+    bool finish() {
+        bool ok = c.sync() && !c.failed();
+        if (timed && ok) { float t = 0; if (cudaEventElapsedTime(&t, e0, e1) == cudaSuccess) c.last_device_ms = t; }
+        if (ok && c.profiling) c.resolve_profile();
+        return ok;
+    }
+    ~Call() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (c.failed()) { cudaStreamSynchronize(c.stream); cudaGetLastError(); }
+    }
+};
+
+const size_t kPad = 64;   // zero bytes after a device text: PLCP's 8-byte windows may over-read
+
+// Copy a host text to a padded, zero-terminated arena buffer.
+void *upload_text(Ctx &c, const void *h, size_t bytes)
+{
+    char *d = (char *)c.alloc(bytes + kPad);
+    if (!d) return nullptr;
+    c.check(cudaMemsetAsync(d + bytes, 0, kPad, c.stream));
+    c.check(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c.stream));
+    return d;
+}
+
+template <typename IDX> void store_freq(Ctx &c, IDX *freq)
+{
+    if (freq) for (int s = 0; s < 256; ++s) freq[s] = (IDX)c.h_scalars[S_FREQ + s];
+}
+
+template <typename IDX> void host_freq(const uint8_t *T, IDX n, IDX *freq)
+{
+    if (!freq) return;
+    for (int s = 0; s < 256; ++s) freq[s] = 0;
+    for (IDX i = 0; i < n; ++i) freq[T[i]]++;
+}
+
+// Device SA (u32) -> host SA of the API's index width.
+template <typename IDX> bool download_indexes(Ctx &c, const u32 *d_src, IDX *h_dst, u64 count, void *scratch8)
+{
+    if (sizeof(IDX) == 4) {
+        return c.check(cudaMemcpyAsync(h_dst, d_src, count * 4, cudaMemcpyDeviceToHost, c.stream));
+    }
+    i64 *wide = (i64 *)scratch8;
+    run_widen(c, d_src, wide, count);
+    return c.check(cudaMemcpyAsync(h_dst, wide, count * 8, cudaMemcpyDeviceToHost, c.stream));
+}
+
+// Host index array (API width) -> device u32 array.
+template <typename IDX> u32 *upload_indexes(Ctx &c, const IDX *h_src, u64 count)
+{
+    u32 *d = c.alloc_n<u32>(count);
+    if (!d) return nullptr;
+    if (sizeof(IDX) == 4) {
+        c.check(cudaMemcpyAsync(d, h_src, count * 4, cudaMemcpyHostToDevice, c.stream));
+    } else {
+        i64 *wide = c.alloc_n<i64>(count);
+        if (!wide) return nullptr;
+        c.check(cudaMemcpyAsync(wide, h_src, count * 8, cudaMemcpyHostToDevice, c.stream));
+        run_narrow(c, wide, d, count);
+    }
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic bodies, IDX = int32_t (libsais_*) or int64_t (libsais64_*)
+// ------------------------------------------------------------------------------------------
+template <typename IDX>
+IDX sa_body(Ctx *c, const uint8_t *T, IDX *SA, IDX n, IDX fs, IDX *freq)
+{
+    if (T == nullptr || SA == nullptr || n < 0 || fs < 0) return -1;
+    if (n < 2) { host_freq(T, n, freq); if (n == 1) SA[0] = 0; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    if (!c->reserve((size_t)n + kPad + sa_workspace_bytes((u64)n, 1) + 4096)) return -2;
+    const u8 *d_T = (const u8 *)upload_text(*c, T, (size_t)n);
+    if (!d_T) return -2;
+    call.start_timer();
+    SAResult res;
+    if (build_sa(*c, d_T, 1, (u64)n, nullptr, &res) != 0) return -2;
+    call.stop_timer();
+    download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
+    if (!call.finish()) return -2;
+    store_freq(*c, freq);
+    return 0;
+}
+
+template <typename IDX, typename SYM>
+IDX sa_int_body(Ctx *c, SYM *T, IDX *SA, IDX n, IDX k, IDX fs)
+{
+    (void)k;                       // the symbol width is measured on the device; k is not trusted
+    if (T == nullptr || SA == nullptr || n < 0 || fs < 0) return -1;
+    if (n < 2) { if (n == 1) SA[0] = 0; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    const size_t tb = (size_t)n * sizeof(SYM);
+    if (!c->reserve(tb + kPad + sa_workspace_bytes((u64)n, (int)sizeof(SYM)) + 4096)) return -2;
+    const void *d_T = upload_text(*c, T, tb);
+    if (!d_T) return -2;
+    call.start_timer();
+    SAResult res;
+    if (build_sa(*c, d_T, (int)sizeof(SYM), (u64)n, nullptr, &res) != 0) return -2;
+    call.stop_timer();
+    download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
+    if (!call.finish()) return -2;
+    return 0;
+}
+
+// BWT with optional aux sampling (r == 0: none).  Returns primary index (r == 0) or 0.
+template <typename IDX>
+IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *freq, IDX r, IDX *I, bool aux)
+{
+    if (T == nullptr || U == nullptr || A == nullptr || n < 0 || fs < 0) return -1;
+    if (aux && (r < 2 || (r & (r - 1)) != 0 || I == nullptr)) return -1;
+    if (n <= 1) {
+        host_freq(T, n, freq);
+        if (n == 1) U[0] = T[0];
+        if (aux) { I[0] = n; return 0; }
+        return n;
+    }
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    const u64 n_aux = aux ? ((u64)n - 1) / (u64)r + 1 : 0;
+    if (!c->reserve((size_t)n * 2 + kPad + n_aux * 4 + sa_workspace_bytes((u64)n, 1) + 8192)) return -2;
+    const u8 *d_T = (const u8 *)upload_text(*c, T, (size_t)n);
+    u8 *d_U = c->alloc_n<u8>((size_t)n);
+    u32 *d_I = n_aux ? c->alloc_n<u32>(n_aux) : nullptr;
+    if (!d_T || !d_U || (n_aux && !d_I)) return -2;
+    call.start_timer();
+    SAResult res;
+    if (build_sa(*c, d_T, 1, (u64)n, nullptr, &res) != 0) return -2;
+    if (run_bwt(*c, d_T, res.SA, res.ISA, d_U, (u64)n, (u64)r, d_I, n_aux) != 0) return -2;
+    call.stop_timer();
+    c->check(cudaMemcpyAsync(U, d_U, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    u32 *h_p0 = (u32 *)(c->h_scalars + S_PRIMARY);
+    c->check(cudaMemcpyAsync(h_p0, res.ISA, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    if (n_aux) download_indexes<IDX>(*c, d_I, I, n_aux, res.scratch);
+    if (!call.finish()) return -2;
+    store_freq(*c, freq);
+    return aux ? 0 : (IDX)((u64)*h_p0 + 1);
+}
+
+template <typename IDX>
+IDX unbwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, const IDX *freq, IDX r, const IDX *I)
+{
+    (void)freq;                    // recomputed on the device (the reference merely trusts it)
+    if (T == nullptr || U == nullptr || A == nullptr || n < 0 || I == nullptr) return -1;
+    if (r != n && (r < 2 || (r & (r - 1)) != 0)) return -1;
+    if (n <= 1) {
+        if (I[0] != n) return -1;
+        if (n == 1) U[0] = T[0];
+        return 0;
+    }
+    for (IDX t = 0; t <= (n - 1) / r; ++t) if (I[t] <= 0 || I[t] > n) return -1;
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    if (!c->reserve((size_t)n * 2 + kPad + unbwt_workspace_bytes((u64)n) + 8192)) return -2;
+    const u8 *d_B = (const u8 *)upload_text(*c, T, (size_t)n);
+    u8 *d_U = c->alloc_n<u8>((size_t)n);
+    if (!d_B || !d_U) return -2;
+    call.start_timer();
+    if (run_unbwt(*c, d_B, d_U, (u64)n, (u64)I[0]) != 0) return -2;
+    call.stop_timer();
+    c->check(cudaMemcpyAsync(U, d_U, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (!call.finish()) return -2;
+    return 0;
+}
+
+template <typename IDX, typename SYM>
+IDX plcp_body(Ctx *c, const SYM *T, const IDX *SA, IDX *PLCP, IDX n)
+{
+    if (T == nullptr || SA == nullptr || PLCP == nullptr || n < 0) return -1;
+    if (n <= 1) { if (n == 1) PLCP[0] = 0; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    const size_t tb = (size_t)n * sizeof(SYM);
+    if (!c->reserve(tb + kPad + (size_t)n * (4 + 4 + 8 + 8) + 8192)) return -2;
+    const void *d_T = upload_text(*c, T, tb);
+    u32 *d_SA = upload_indexes<IDX>(*c, SA, (u64)n);
+    u32 *d_P = c->alloc_n<u32>((size_t)n);
+    void *wide = sizeof(IDX) == 8 ? c->alloc((size_t)n * 8) : nullptr;
+    if (!d_T || !d_SA || !d_P || (sizeof(IDX) == 8 && !wide)) return -2;
+    call.start_timer();
+    if (run_plcp(*c, d_T, (int)sizeof(SYM), d_SA, d_P, (u64)n) != 0) return -2;
+    call.stop_timer();
+    download_indexes<IDX>(*c, d_P, PLCP, (u64)n, wide);
+    if (!call.finish()) return -2;
+    return 0;
+}
+
+template <typename IDX>
+IDX lcp_body(Ctx *c, const IDX *PLCP, const IDX *SA, IDX *LCP, IDX n)
+{
+    if (PLCP == nullptr || SA == nullptr || LCP == nullptr || n < 0) return -1;
+    if (n <= 1) { if (n == 1) LCP[0] = PLCP[SA[0]]; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    if (!c->reserve((size_t)n * (4 + 4 + 4 + 8 + 8 + 8) + 8192)) return -2;
+    u32 *d_P = upload_indexes<IDX>(*c, PLCP, (u64)n);
+    u32 *d_SA = upload_indexes<IDX>(*c, SA, (u64)n);
+    u32 *d_L = c->alloc_n<u32>((size_t)n);
+    void *wide = sizeof(IDX) == 8 ? c->alloc((size_t)n * 8) : nullptr;
+    if (!d_P || !d_SA || !d_L || (sizeof(IDX) == 8 && !wide)) return -2;
+    call.start_timer();
+    if (run_lcp(*c, d_P, d_SA, d_L, (u64)n) != 0) return -2;
+    call.stop_timer();
+    download_indexes<IDX>(*c, d_L, LCP, (u64)n, wide);   // LCP may alias SA: SA was consumed above
+    if (!call.finish()) return -2;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ contexts
+void *libsais_create_ctx(void) { return new_ctx(-1); }
+void *libsais_create_ctx_omp(int32_t threads) { return threads < 0 ? nullptr : new_ctx(-1); }
+void libsais_free_ctx(void *ctx) { if (ctx) { Ctx *c = as_ctx(ctx); c->destroy(); delete c; } }
+void *libsais_unbwt_create_ctx(void) { return new_ctx(-1); }
+void *libsais_unbwt_create_ctx_omp(int32_t threads) { return threads < 0 ? nullptr : new_ctx(-1); }
+void libsais_unbwt_free_ctx(void *ctx) { libsais_free_ctx(ctx); }
+
+// ------------------------------------------------------------------ libsais (int32)
+int32_t libsais(const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq)
+{ return sa_body<int32_t>(default_ctx(), T, SA, n, fs, freq); }
+int32_t libsais_ctx(const void *ctx, const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq)
+{ if (ctx == nullptr) return -1; return sa_body<int32_t>(as_ctx(ctx), T, SA, n, fs, freq); }
+int32_t libsais_omp(const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq, int32_t threads)
+{ if (threads < 0) return -1; return sa_body<int32_t>(default_ctx(), T, SA, n, fs, freq); }
+
+int32_t libsais_int(int32_t *T, int32_t *SA, int32_t n, int32_t k, int32_t fs)
+{ return sa_int_body<int32_t, int32_t>(default_ctx(), T, SA, n, k, fs); }
+int32_t libsais_int_omp(int32_t *T, int32_t *SA, int32_t n, int32_t k, int32_t fs, int32_t threads)
+{ if (threads < 0) return -1; return sa_int_body<int32_t, int32_t>(default_ctx(), T, SA, n, k, fs); }
+
+// generalized suffix arrays: exported so existing programs link; not supported yet
+int32_t libsais_gsa(const uint8_t *, int32_t *, int32_t, int32_t, int32_t *) { return -1; }
+int32_t libsais_gsa_ctx(const void *, const uint8_t *, int32_t *, int32_t, int32_t, int32_t *) { return -1; }
+int32_t libsais_gsa_omp(const uint8_t *, int32_t *, int32_t, int32_t, int32_t *, int32_t) { return -1; }
+int32_t libsais_plcp_gsa(const uint8_t *, const int32_t *, int32_t *, int32_t) { return -1; }
+int32_t libsais_plcp_gsa_omp(const uint8_t *, const int32_t *, int32_t *, int32_t, int32_t) { return -1; }
+
+int32_t libsais_bwt(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq)
+{ return bwt_body<int32_t>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }
+int32_t libsais_bwt_aux(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq, int32_t r, int32_t *I)
+{ return bwt_body<int32_t>(default_ctx(), T, U, A, n, fs, freq, r, I, true); }
+int32_t libsais_bwt_ctx(const void *ctx, const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq)
+{ if (ctx == nullptr) return -1; return bwt_body<int32_t>(as_ctx(ctx), T, U, A, n, fs, freq, 0, nullptr, false); }
+int32_t libsais_bwt_aux_ctx(const void *ctx, const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq, int32_t r, int32_t *I)
+{ if (ctx == nullptr) return -1; return bwt_body<int32_t>(as_ctx(ctx), T, U, A, n, fs, freq, r, I, true); }
+int32_t libsais_bwt_omp(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq, int32_t threads)
+{ if (threads < 0) return -1; return bwt_body<int32_t>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }
+int32_t libsais_bwt_aux_omp(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq, int32_t r, int32_t *I, int32_t threads)
+{ if (threads < 0) return -1; return bwt_body<int32_t>(default_ctx(), T, U, A, n, fs, freq, r, I, true); }
+
+int32_t libsais_unbwt(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t i)
+{ return unbwt_body<int32_t>(default_ctx(), T, U, A, n, freq, n, &i); }
+int32_t libsais_unbwt_ctx(const void *ctx, const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t i)
+{ if (ctx == nullptr) return -1; return unbwt_body<int32_t>(as_ctx(ctx), T, U, A, n, freq, n, &i); }
+int32_t libsais_unbwt_aux(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t r, const int32_t *I)
+{ return unbwt_body<int32_t>(default_ctx(), T, U, A, n, freq, r, I); }
+int32_t libsais_unbwt_aux_ctx(const void *ctx, const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t r, const int32_t *I)
+{ if (ctx == nullptr) return -1; return unbwt_body<int32_t>(as_ctx(ctx), T, U, A, n, freq, r, I); }
+int32_t libsais_unbwt_omp(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t i, int32_t threads)
+{ if (threads < 0) return -1; return unbwt_body<int32_t>(default_ctx(), T, U, A, n, freq, n, &i); }
+int32_t libsais_unbwt_aux_omp(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t r, const int32_t *I, int32_t threads)
+{ if (threads < 0) return -1; return unbwt_body<int32_t>(default_ctx(), T, U, A, n, freq, r, I); }
+
+int32_t libsais_plcp(const uint8_t *T, const int32_t *SA, int32_t *PLCP, int32_t n)
+{ return plcp_body<int32_t, uint8_t>(default_ctx(), T, SA, PLCP, n); }
+int32_t libsais_plcp_int(const int32_t *T, const int32_t *SA, int32_t *PLCP, int32_t n)
+{ return plcp_body<int32_t, int32_t>(default_ctx(), T, SA, PLCP, n); }
+int32_t libsais_lcp(const int32_t *PLCP, const int32_t *SA, int32_t *LCP, int32_t n)
+{ return lcp_body<int32_t>(default_ctx(), PLCP, SA, LCP, n); }
+int32_t libsais_plcp_omp(const uint8_t *T, const int32_t *SA, int32_t *PLCP, int32_t n, int32_t threads)
+{ if (threads < 0) return -1; return plcp_body<int32_t, uint8_t>(default_ctx(), T, SA, PLCP, n); }
+int32_t libsais_plcp_int_omp(const int32_t *T, const int32_t *SA, int32_t *PLCP, int32_t n, int32_t threads)
+{ if (threads < 0) return -1; return plcp_body<int32_t, int32_t>(default_ctx(), T, SA, PLCP, n); }
+int32_t libsais_lcp_omp(const int32_t *PLCP, const int32_t *SA, int32_t *LCP, int32_t n, int32_t threads)
+{ if (threads < 0) return -1; return lcp_body<int32_t>(default_ctx(), PLCP, SA, LCP, n); }
+
+// ------------------------------------------------------------------ libsais64 (int64)
+int64_t libsais64(const uint8_t *T, int64_t *SA, int64_t n, int64_t fs, int64_t *freq)
+{ return sa_body<int64_t>(default_ctx(), T, SA, n, fs, freq); }
+int64_t libsais64_omp(const uint8_t *T, int64_t *SA, int64_t n, int64_t fs, int64_t *freq, int64_t threads)
+{ if (threads < 0) return -1; return sa_body<int64_t>(default_ctx(), T, SA, n, fs, freq); }
+int64_t libsais64_long(int64_t *T, int64_t *SA, int64_t n, int64_t k, int64_t fs)
+{ return sa_int_body<int64_t, int64_t>(default_ctx(), T, SA, n, k, fs); }
+int64_t libsais64_long_omp(int64_t *T, int64_t *SA, int64_t n, int64_t k, int64_t fs, int64_t threads)
+{ if (threads < 0) return -1; return sa_int_body<int64_t, int64_t>(default_ctx(), T, SA, n, k, fs); }
+
+int64_t libsais64_gsa(const uint8_t *, int64_t *, int64_t, int64_t, int64_t *) { return -1; }
+int64_t libsais64_gsa_omp(const uint8_t *, int64_t *, int64_t, int64_t, int64_t *, int64_t) { return -1; }
+int64_t libsais64_plcp_gsa(const uint8_t *, const int64_t *, int64_t *, int64_t) { return -1; }
+int64_t libsais64_plcp_gsa_omp(const uint8_t *, const int64_t *, int64_t *, int64_t, int64_t) { return -1; }
+
+int64_t libsais64_bwt(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, int64_t fs, int64_t *freq)
+{ return bwt_body<int64_t>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }
+int64_t libsais64_bwt_aux(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, int64_t fs, int64_t *freq, int64_t r, int64_t *I)
+{ return bwt_body<int64_t>(default_ctx(), T, U, A, n, fs, freq, r, I, true); }
+int64_t libsais64_bwt_omp(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, int64_t fs, int64_t *freq, int64_t threads)
+{ if (threads < 0) return -1; return bwt_body<int64_t>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }
+int64_t libsais64_bwt_aux_omp(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, int64_t fs, int64_t *freq, int64_t r, int64_t *I, int64_t threads)
+{ if (threads < 0) return -1; return bwt_body<int64_t>(default_ctx(), T, U, A, n, fs, freq, r, I, true); }
+
+int64_t libsais64_unbwt(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, const int64_t *freq, int64_t i)
+{ return unbwt_body<int64_t>(default_ctx(), T, U, A, n, freq, n, &i); }
+int64_t libsais64_unbwt_aux(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, const int64_t *freq, int64_t r, const int64_t *I)
+{ return unbwt_body<int64_t>(default_ctx(), T, U, A, n, freq, r, I); }
+int64_t libsais64_unbwt_omp(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, const int64_t *freq, int64_t i, int64_t threads)
+{ if (threads < 0) return -1; return unbwt_body<int64_t>(default_ctx(), T, U, A, n, freq, n, &i); }
+int64_t libsais64_unbwt_aux_omp(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, const int64_t *freq, int64_t r, const int64_t *I, int64_t threads)
+{ if (threads < 0) return -1; return unbwt_body<int64_t>(default_ctx(), T, U, A, n, freq, r, I); }
+
+int64_t libsais64_plcp(const uint8_t *T, const int64_t *SA, int64_t *PLCP, int64_t n)
+{ return plcp_body<int64_t, uint8_t>(default_ctx(), T, SA, PLCP, n); }
+int64_t libsais64_lcp(const int64_t *PLCP, const int64_t *SA, int64_t *LCP, int64_t n)
+{ return lcp_body<int64_t>(default_ctx(), PLCP, SA, LCP, n); }
+int64_t libsais64_plcp_omp(const uint8_t *T, const int64_t *SA, int64_t *PLCP, int64_t n, int64_t threads)
+{ if (threads < 0) return -1; return plcp_body<int64_t, uint8_t>(default_ctx(), T, SA, PLCP, n); }
+int64_t libsais64_lcp_omp(const int64_t *PLCP, const int64_t *SA, int64_t *LCP, int64_t n, int64_t threads)
+{ if (threads < 0) return -1; return lcp_body<int64_t>(default_ctx(), PLCP, SA, LCP, n); }
+
+// ------------------------------------------------------------------ extras (libsais_cuda.h)
+int32_t libsais_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+void *libsais_cuda_create_ctx(int32_t device) { return new_ctx(device); }
+void *libsais_cuda_stream(const void *ctx) { Ctx *c = ctx ? as_ctx(ctx) : default_ctx(); return c ? (void *)c->stream : nullptr; }
+int32_t libsais_cuda_set_profiling(const void *ctx, int32_t on)
+{ Ctx *c = ctx ? as_ctx(ctx) : default_ctx(); if (!c) return -2; c->profiling = on != 0; return 0; }
+
+int32_t libsais_cuda_get_stats(const void *ctx, libsais_cuda_stats *out)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !out) return -1;
+    std::memset(out, 0, sizeof(*out));
+    out->n_classes = KC_COUNT;
+    out->n_rounds = (int32_t)c->rounds.size();
+    out->total_launches = c->total_launches;
+    for (int i = 0; i < KC_COUNT; ++i) { out->launches[i] = c->launches[i]; out->ms[i] = c->ms[i]; out->bytes[i] = c->bytes[i]; }
+    out->device_ms = c->last_device_ms;
+    out->workspace_bytes = c->ws_cap;
+    return 0;
+}
+int32_t libsais_cuda_get_round(const void *ctx, int32_t round, libsais_cuda_round *out)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !out || round < 0 || (size_t)round >= c->rounds.size()) return -1;
+    const RoundStat &r = c->rounds[round];
+    out->h = r.h; out->n_active = r.n_active; out->n_groups = r.n_groups; out->passes = r.passes; out->key_bits = r.key_bits;
+    return 0;
+}
+const char *libsais_cuda_kernel_class_name(int32_t kc) { return kc >= 0 && kc < KC_COUNT ? kKernelClassName[kc] : ""; }
+int32_t libsais_cuda_last_error(const void *ctx) { Ctx *c = ctx ? as_ctx(ctx) : default_ctx(); return c ? (int32_t)c->last_error : -1; }
+
+int64_t libsais_cuda_sa_dev(const void *ctx, const uint8_t *d_T, uint32_t *d_SA, int64_t n)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (d_T == nullptr || d_SA == nullptr || n < 0) return -1;
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    if (n == 0) return 0;
+    Call call(*c);
+    if (!c->reserve(sa_workspace_bytes((u64)n, 1) + 4096)) return -2;
+    call.start_timer();
+    SAResult res;
+    if (build_sa(*c, d_T, 1, (u64)n, d_SA, &res) != 0) return -2;
+    call.stop_timer();
+    return call.finish() ? 0 : -2;
+}
+
+int64_t libsais_cuda_bwt_dev(const void *ctx, const uint8_t *d_T, uint8_t *d_U, int64_t n)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (d_T == nullptr || d_U == nullptr || n < 0) return -1;
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    if (n == 0) return 0;
+    Call call(*c);
+    if (!c->reserve(sa_workspace_bytes((u64)n, 1) + 4096)) return -2;
+    call.start_timer();
+    SAResult res;
+    if (build_sa(*c, d_T, 1, (u64)n, nullptr, &res) != 0) return -2;
+    if (run_bwt(*c, d_T, res.SA, res.ISA, d_U, (u64)n, 0, nullptr, 0) != 0) return -2;
+    call.stop_timer();
+    u32 *h_p0 = (u32 *)(c->h_scalars + S_PRIMARY);
+    c->check(cudaMemcpyAsync(h_p0, res.ISA, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    if (!call.finish()) return -2;
+    return (int64_t)*h_p0 + 1;
+}
+
+int64_t libsais_cuda_plcp_dev(const void *ctx, const uint8_t *d_T, const uint32_t *d_SA, uint32_t *d_PLCP, int64_t n)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (d_T == nullptr || d_SA == nullptr || d_PLCP == nullptr || n < 0) return -1;
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    if (n == 0) return 0;
+    Call call(*c);
+    if (!c->reserve((size_t)n + kPad + 4096)) return -2;
+    // own padded copy of the text: the compare kernel's 8-byte windows read past the end
+    u8 *d_Tp = c->alloc_n<u8>((size_t)n + kPad);
+    if (!d_Tp) return -2;
+    call.start_timer();
+    c->check(cudaMemsetAsync(d_Tp + n, 0, kPad, c->stream));
+    c->check(cudaMemcpyAsync(d_Tp, d_T, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    if (run_plcp(*c, d_Tp, 1, d_SA, d_PLCP, (u64)n) != 0) return -2;
+    call.stop_timer();
+    return call.finish() ? 0 : -2;
+}
+
+int64_t libsais_cuda_lcp_dev(const void *ctx, const uint32_t *d_PLCP, const uint32_t *d_SA, uint32_t *d_LCP, int64_t n)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (d_PLCP == nullptr || d_SA == nullptr || d_LCP == nullptr || n < 0) return -1;
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    if (n == 0) return 0;
+    Call call(*c);
+    call.start_timer();
+    if (run_lcp(*c, d_PLCP, d_SA, d_LCP, (u64)n) != 0) return -2;
+    call.stop_timer();
+    return call.finish() ? 0 : -2;
+}
+
+int64_t libsais_cuda_unbwt_dev(const void *ctx, const uint8_t *d_B, uint8_t *d_U, int64_t n, int64_t primary)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (d_B == nullptr || d_U == nullptr || n < 0) return -1;
+    if (n == 0) return primary == 0 ? 0 : -1;
+    if (primary < 1 || primary > n) return -1;
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    if (!c->reserve(unbwt_workspace_bytes((u64)n) + 8192)) return -2;
+    call.start_timer();
+    if (run_unbwt(*c, d_B, d_U, (u64)n, (u64)primary) != 0) return -2;
+    call.stop_timer();
+    return call.finish() ? 0 : -2;
+}
+
+}  // extern "C"

@@ -1,0 +1,281 @@
+// post.cu -- the stages that consume a suffix array: BWT (+primary, aux), phi / PLCP / LCP,
+// and the inverse BWT.  Definitions follow SURVEY.md §8a; each kernel cites the reference
+// region whose result it reproduces bit-exactly.
+#include "core.h"
+#include "radix_sort.cuh"
+
+namespace lsc {
+
+// ---------------------------------------------------------------------------------------------
+// BWT gather.  Reference: final_bwt_scan_* + bwt_copy_8u, src/libsais.c:4777-4797, :5396-5422,
+// :6960-7006, assembly :7110-7118.  With p0 = ISA[0]:  U[0] = T[n-1];  slot i != p0 writes
+// T[SA[i]-1] to U[i + (i < p0)].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bwt_kernel(const u8 *__restrict__ T, const u32 *__restrict__ SA, const u32 *__restrict__ ISA,
+           u8 *__restrict__ U, u64 n)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const u64 p0 = ISA[0];
+    if (i == 0) U[0] = T[n - 1];
+    u32 s = ld_stream(SA + i);
+    if (s != 0) U[i + (i < p0 ? 1 : 0)] = T[s - 1];
+}
+
+// aux indexes: I[j] = ISA[j*r] + 1   (reference :4811, :5286, :5437)
+__global__ void __launch_bounds__(256)
+bwt_aux_kernel(const u32 *__restrict__ ISA, u64 r, u32 *__restrict__ I, u64 n_aux)
+{
+    u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j < n_aux) I[j] = ISA[j * r] + 1;
+}
+
+int run_bwt(Ctx &c, const u8 *d_T, const u32 *d_SA, const u32 *d_ISA, u8 *d_U, u64 n,
+            u64 r, u32 *d_I, u64 n_aux)
+{
+    LSC_LAUNCH(c, KC_BWT, (double)n * 6, bwt_kernel, (u32)ceil_div(n, 256), 256, 0, d_T, d_SA, d_ISA, d_U, n);
+    if (d_I && n_aux)
+        LSC_LAUNCH(c, KC_BWT, (double)n_aux * 8, bwt_aux_kernel, (u32)ceil_div(n_aux, 256), 256, 0, d_ISA, r, d_I, n_aux);
+    return c.failed() ? -2 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phi scatter (reference compute_phi :8116-8142): PLCP[SA[i]] = SA[i-1], PLCP[SA[0]] = n.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+phi_kernel(const u32 *__restrict__ SA, u32 *__restrict__ PHI, u64 n)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    u32 s = SA[i];
+    if (s < n) PHI[s] = i ? SA[i - 1] : (u32)n;        // a corrupt SA must not write out of bounds
+}
+
+// ---------------------------------------------------------------------------------------------
+// PLCP compare (reference compute_plcp :8167-8190, _int :8263-8286): in text order,
+// PLCP[i] = lcp(T[i..], T[phi[i]..]) with the Kasai carry PLCP[i] >= PLCP[i-1]-1 kept inside
+// each thread's chunk of consecutive positions; bytes are compared 8 at a time through
+// unaligned 64-bit windows assembled from aligned loads.
+// ---------------------------------------------------------------------------------------------
+static const int kPlcpChunk = 32;
+
+__device__ __forceinline__ u64 window64(const u64 *__restrict__ W, u64 pos)
+{
+    u64 q = pos >> 3; int sh = (int)(pos & 7) * 8;
+    u64 lo = W[q];
+    if (sh == 0) return lo;
+    u64 hi = W[q + 1];
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
+template <int SYM_BYTES>
+__global__ void __launch_bounds__(128)
+plcp_kernel(const void *__restrict__ Tv, u32 *__restrict__ PLCP, u64 n)
+{
+    u64 t = (u64)blockIdx.x * 128 + threadIdx.x;
+    u64 begin = t * kPlcpChunk;
+    if (begin >= n) return;
+    u64 end = begin + kPlcpChunk < n ? begin + kPlcpChunk : n;
+    u64 l = 0;
+    for (u64 i = begin; i < end; ++i) {
+        u64 k = PLCP[i];
+        if (k >= n) { l = 0; }
+        else {
+            u64 lim = n - (i > k ? i : k);               // symbols available to both suffixes
+            if (SYM_BYTES == 1) {
+                const u64 *W = (const u64 *)Tv;
+                while (l < lim) {
+                    u64 x = window64(W, i + l) ^ window64(W, k + l);
+                    if (x) { l += (u64)((__ffsll((long long)x) - 1) >> 3); break; }
+                    l += 8;
+                }
+            } else {
+                const u32 *S = (const u32 *)Tv;
+                while (l < lim && S[i + l] == S[k + l]) ++l;
+            }
+            if (l > lim) l = lim;
+        }
+        PLCP[i] = (u32)l;
+        if (l) --l;
+    }
+}
+
+int run_plcp(Ctx &c, const void *d_T, int sym_bytes, const u32 *d_SA, u32 *d_PLCP, u64 n)
+{
+    LSC_LAUNCH(c, KC_PHI, (double)n * 8, phi_kernel, (u32)ceil_div(n, 256), 256, 0, d_SA, d_PLCP, n);
+    u64 threads = ceil_div(n, kPlcpChunk);
+    if (sym_bytes == 1)
+        LSC_LAUNCH(c, KC_PLCP, (double)n * 11, plcp_kernel<1>, (u32)ceil_div(threads, 128), 128, 0, d_T, d_PLCP, n);
+    else
+        LSC_LAUNCH(c, KC_PLCP, (double)n * 16, plcp_kernel<4>, (u32)ceil_div(threads, 128), 128, 0, d_T, d_PLCP, n);
+    return c.failed() ? -2 : 0;
+}
+
+// LCP permute (reference compute_lcp :8311-8338): LCP[i] = PLCP[SA[i]]
+__global__ void __launch_bounds__(256)
+lcp_kernel(const u32 *__restrict__ PLCP, const u32 *__restrict__ SA, u32 *__restrict__ LCP, u64 n)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) { u32 s = ld_stream(SA + i); LCP[i] = s < n ? PLCP[s] : 0; }
+}
+
+int run_lcp(Ctx &c, const u32 *d_PLCP, const u32 *d_SA, u32 *d_LCP, u64 n)
+{
+    LSC_LAUNCH(c, KC_LCP, (double)n * 12, lcp_kernel, (u32)ceil_div(n, 256), 256, 0, d_PLCP, d_SA, d_LCP, n);
+    return c.failed() ? -2 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inverse BWT.  Reference: libsais_unbwt_* src/libsais.c:7362-8112 (bigram psi + a sequential
+// pointer chase).  Here: rows 0..n are the sorted rotations of T$, the "$" row is `primary`,
+// L'[row] = B[row - (row > primary)].  One stable counting-sort pass of the row ids by symbol
+// (the onesweep pass) yields psi: psi[j+1] = j-th row in symbol order, F[j+1] = its symbol.
+// The text is the walk x0 = primary, x(t+1) = psi[x(t)], T[t] = F[x(t)], ending at row 0.
+// The single n-step chain is cut at splitter rows (row % S == 0, plus the start): every
+// splitter walks to the next one (phase 1), the splitters are list-ranked by pointer jumping
+// (phase 2), and every splitter re-walks its piece writing text at its now-known offset.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+unbwt_rows_kernel(u32 *__restrict__ rows, u64 n, u64 primary)
+{
+    u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (e < n) rows[e] = (u32)(e + (e >= primary ? 1 : 0));
+}
+
+static const u32 kEndMark = 0xFFFFFFFFu;
+
+__device__ __forceinline__ bool unbwt_stop(u64 x, u64 smask, u64 primary)
+{
+    return x == 0 || (x & smask) == 0 || x == primary;
+}
+
+// phase 1: splitter id 0 = the start row `primary`; id s >= 1 = row s*S.
+__global__ void __launch_bounds__(128)
+unbwt_walk1_kernel(const u32 *__restrict__ psi, u64 n, u64 primary, int logS, u64 nsplit,
+                   u32 *__restrict__ nxt, u32 *__restrict__ len)
+{
+    u64 id = (u64)blockIdx.x * 128 + threadIdx.x;
+    if (id >= nsplit) return;
+    const u64 smask = ((u64)1 << logS) - 1;
+    u64 x = id ? (id << logS) : primary;
+    u32 steps = 0;
+    do { x = psi[x]; ++steps; } while (!unbwt_stop(x, smask, primary) && steps <= n);
+    len[id] = steps;
+    nxt[id] = (x == 0) ? kEndMark : (x == primary ? 0u : (u32)(x >> logS));
+}
+
+// phase 2: one pointer-jumping round (double buffered): dist = characters from here to the end
+__global__ void __launch_bounds__(256)
+unbwt_jump_kernel(const u32 *__restrict__ nxt_in, const u64 *__restrict__ dist_in,
+                  u32 *__restrict__ nxt_out, u64 *__restrict__ dist_out, u64 nsplit)
+{
+    u64 id = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (id >= nsplit) return;
+    u32 nx = nxt_in[id]; u64 d = dist_in[id];
+    if (nx != kEndMark) { d += dist_in[nx]; nx = nxt_in[nx]; }
+    nxt_out[id] = nx; dist_out[id] = d;
+}
+
+__global__ void __launch_bounds__(256)
+unbwt_dist_init_kernel(const u32 *__restrict__ len, u64 *__restrict__ dist, u64 nsplit)
+{
+    u64 id = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (id < nsplit) dist[id] = len[id];
+}
+
+// phase 3: re-walk, emit text.  cum[c] = 1 + #{symbols < c} (row of the first rotation starting with c)
+__global__ void __launch_bounds__(128)
+unbwt_walk2_kernel(const u32 *__restrict__ psi, const u64 *__restrict__ base, u64 n, u64 primary,
+                   int logS, u64 nsplit, const u64 *__restrict__ dist, u8 *__restrict__ U)
+{
+    __shared__ u64 cum[257];
+    for (int i = threadIdx.x; i < 256; i += 128) cum[i] = base[i] + 1;
+    if (threadIdx.x == 0) cum[256] = n + 1;
+    __syncthreads();
+    u64 id = (u64)blockIdx.x * 128 + threadIdx.x;
+    if (id >= nsplit) return;
+    const u64 smask = ((u64)1 << logS) - 1;
+    u64 x = id ? (id << logS) : primary;
+    u64 d = dist[id];
+    if (d > n) return;                                   // inconsistent input: never write out of bounds
+    u64 t = n - d;
+    u64 steps = 0;
+    do {
+        // F[x]: largest c with cum[c] <= x
+        int lo = 0, hi = 256;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (cum[mid] <= x) lo = mid; else hi = mid; }
+        if (t < n) U[t] = (u8)lo;
+        ++t; ++steps;
+        x = psi[x];
+    } while (!unbwt_stop(x, smask, primary) && steps <= n);
+}
+
+static int unbwt_log_s(u64 n) { return n >= (1ull << 24) ? 7 : 5; }
+
+size_t unbwt_workspace_bytes(u64 n)
+{
+    u64 ns = (n >> unbwt_log_s(n)) + 2;
+    return (size_t)n * (4 + 4 + 1) + 8 + RadixSort<u8, u32>::temp_bytes(n) + ns * (4 + 4 + 4 + 8 + 8) + 16 * 256;
+}
+
+int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary)
+{
+    const int logS = unbwt_log_s(n);
+    const u64 nsplit = (n >> logS) + 1;
+    u32 *rows = c.alloc_n<u32>(n);
+    u32 *psi = c.alloc_n<u32>(n + 1);
+    u8 *keys_out = c.alloc_n<u8>(n);
+    void *temp = c.alloc(RadixSort<u8, u32>::temp_bytes(n));
+    u32 *nxt0 = c.alloc_n<u32>(nsplit), *nxt1 = c.alloc_n<u32>(nsplit), *len = c.alloc_n<u32>(nsplit);
+    u64 *dist0 = c.alloc_n<u64>(nsplit), *dist1 = c.alloc_n<u64>(nsplit);
+    if (!rows || !psi || !keys_out || !temp || !dist1) return -2;
+    u32 *err = (u32 *)(c.d_scalars + S_ERR);
+    c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, sizeof(u64), c.stream));
+    c.check(cudaMemsetAsync(psi, 0, sizeof(u32), c.stream));
+
+    LSC_LAUNCH(c, KC_UNBWT_PREP, (double)n * 4, unbwt_rows_kernel, (u32)ceil_div(n, 256), 256, 0, rows, n, primary);
+    // one stable 8-bit pass: (symbol, row) -> psi[1..n]; the pass's digit bases are 1-based F boundaries
+    int where = RadixSort<u8, u32>::sort(c, const_cast<u8 *>(d_B), rows, keys_out, psi + 1, n, 0, 8, temp, err);
+    if (where != 1) return -2;
+    const u64 *base = (const u64 *)((char *)temp + kMaxPasses * kRadixSize * sizeof(u64));
+
+    LSC_LAUNCH(c, KC_UNBWT_WALK, (double)n * 4, unbwt_walk1_kernel, (u32)ceil_div(nsplit, 128), 128, 0,
+               psi, n, primary, logS, nsplit, nxt0, len);
+    LSC_LAUNCH(c, KC_UNBWT_RANK, (double)nsplit * 12, unbwt_dist_init_kernel, (u32)ceil_div(nsplit, 256), 256, 0, len, dist0, nsplit);
+    int rounds = bits_for(nsplit) + 1;
+    u32 *ni = nxt0, *no = nxt1; u64 *di = dist0, *dout = dist1;
+    for (int r = 0; r < rounds; ++r) {
+        LSC_LAUNCH(c, KC_UNBWT_RANK, (double)nsplit * 24, unbwt_jump_kernel, (u32)ceil_div(nsplit, 256), 256, 0,
+                   ni, di, no, dout, nsplit);
+        u32 *tn = ni; ni = no; no = tn;
+        u64 *td = di; di = dout; dout = td;
+    }
+    LSC_LAUNCH(c, KC_UNBWT_WALK, (double)n * 5, unbwt_walk2_kernel, (u32)ceil_div(nsplit, 128), 128, 0,
+               psi, base, n, primary, logS, nsplit, di, d_U);
+    return c.failed() ? -2 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// index-width conversion for the libsais64 API (reference converters src/libsais64.c:6638-6701)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) widen_kernel(const u32 *__restrict__ src, i64 *__restrict__ dst, u64 n)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = (i64)src[i];
+}
+__global__ void __launch_bounds__(256) narrow_kernel(const i64 *__restrict__ src, u32 *__restrict__ dst, u64 n)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = (u32)src[i];
+}
+void run_widen(Ctx &c, const u32 *src, i64 *dst, u64 n)
+{
+    if (n) LSC_LAUNCH(c, KC_CONVERT, (double)n * 12, widen_kernel, (u32)ceil_div(n, 256), 256, 0, src, dst, n);
+}
+void run_narrow(Ctx &c, const i64 *src, u32 *dst, u64 n)
+{
+    if (n) LSC_LAUNCH(c, KC_CONVERT, (double)n * 12, narrow_kernel, (u32)ceil_div(n, 256), 256, 0, src, dst, n);
+}
+
+}  // namespace lsc

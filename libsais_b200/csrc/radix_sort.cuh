@@ -1,0 +1,314 @@
+// radix_sort.cuh -- hand-written onesweep LSD radix sort for (key, value) pairs on sm_100a.
+//
+// One upfront kernel builds the histograms of every digit; each digit pass is then ONE kernel
+// that reads the tile once and writes it once ("onesweep"): warp-level multisplit with
+// match.any, a chained scan over tiles with decoupled look-back per digit, staging of the
+// tile in shared memory so the scatter leaves the SM as runs of consecutive addresses.
+// Stable; tiles are claimed through an atomic ticket so a tile's predecessors are always
+// resident (forward progress of the look-back).
+//
+// Replaces, as the ordering engine of the SA core, the reference's induced-sorting scans
+// (reference src/libsais.c:2157-4101 and :4777-6265); see DESIGN.md §3.
+#pragma once
+#include "common.cuh"
+#include "ctx.h"
+
+namespace lsc {
+
+static const int kRadixBits = 8;
+static const int kRadixSize = 256;
+static const int kMaxPasses = 16;
+
+static const u64 kStFlagAgg  = 1ull << 62;   // tile aggregate published
+static const u64 kStFlagInc  = 2ull << 62;   // inclusive prefix published
+static const u64 kStValMask  = (1ull << 62) - 1;
+static const u32 kSpinLimit  = 1u << 27;     // look-back watchdog: flag an error instead of hanging the GPU
+
+struct SortPlan {
+    int passes;
+    int shift[kMaxPasses];
+    int nbits[kMaxPasses];
+};
+
+static inline SortPlan make_sort_plan(int lo_bit, int hi_bit)
+{
+    SortPlan p; p.passes = 0;
+    int bits = hi_bit - lo_bit;
+    if (bits <= 0) return p;
+    int P = (bits + kRadixBits - 1) / kRadixBits;
+    int base = bits / P, rem = bits % P, s = lo_bit;
+    for (int i = 0; i < P; ++i) {
+        int nb = base + (i < rem ? 1 : 0);
+        p.shift[i] = s; p.nbits[i] = nb; s += nb;
+    }
+    p.passes = P;
+    return p;
+}
+
+template <typename KeyT>
+__device__ __forceinline__ u32 digit_of(KeyT k, int shift, u32 mask) { return (u32)(k >> shift) & mask; }
+
+// ---------------------------------------------------------------------------------------------
+// Upfront histograms of all digits: hist[pass][256] (u64).  One read of the keys.
+// ---------------------------------------------------------------------------------------------
+template <typename KeyT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+sort_hist_kernel(const KeyT *__restrict__ keys, u64 n, SortPlan plan, u64 *__restrict__ hist)
+{
+    __shared__ u32 sh[kMaxPasses * kRadixSize];
+    const int P = plan.passes;
+    for (int i = threadIdx.x; i < P * kRadixSize; i += THREADS) sh[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * THREADS;
+    const u64 rounds = (n + stride - 1) / stride;
+    for (u64 r = 0; r < rounds; ++r) {
+        u64 idx = r * stride + (u64)blockIdx.x * THREADS + threadIdx.x;
+        bool valid = idx < n;
+        KeyT k = valid ? keys[idx] : (KeyT)0;
+        for (int p = 0; p < P; ++p) {
+            u32 d = digit_of(k, plan.shift[p], (1u << plan.nbits[p]) - 1);
+            u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+            // skew fast path: a warp whose keys all share the digit issues one add, not 32 serialised ones
+            if (__all_sync(0xffffffffu, valid && d == d0)) {
+                if ((threadIdx.x & 31) == 0) atomicAdd(&sh[p * kRadixSize + d0], 32u);
+            } else if (valid) {
+                atomicAdd(&sh[p * kRadixSize + d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * kRadixSize; i += THREADS) {
+        u32 c = sh[i];
+        if (c) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)c);
+    }
+}
+
+// Exclusive scan of each pass's histogram -> global base offset of every digit.  grid = passes.
+static __global__ void sort_scan_kernel(const u64 *__restrict__ hist, u64 *__restrict__ base)
+{
+    __shared__ u64 s[kRadixSize];
+    const int t = threadIdx.x;
+    u64 v = hist[blockIdx.x * kRadixSize + t];
+    s[t] = v;
+    __syncthreads();
+    for (int off = 1; off < kRadixSize; off <<= 1) {
+        u64 add = t >= off ? s[t - off] : 0;
+        __syncthreads();
+        s[t] += add;
+        __syncthreads();
+    }
+    base[blockIdx.x * kRadixSize + t] = s[t] - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One digit pass.
+// ---------------------------------------------------------------------------------------------
+template <typename KeyT, typename ValT, int THREADS, int IPT>
+struct PassSmem {
+    static const int TILE = THREADS * IPT;
+    KeyT keys[TILE];
+    u64  goff[kRadixSize];                 // global offset of a digit's run minus its offset in the tile
+    ValT vals[TILE];
+    u32  whist[(THREADS / 32) * kRadixSize];
+    u32  tileoff[kRadixSize];
+    u32  scan_tmp[32];
+    u32  tile;
+};
+
+template <typename KeyT, typename ValT, int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS)
+sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
+                 KeyT *__restrict__ kout, ValT *__restrict__ vout, u64 n,
+                 int shift, u32 dmask, const u64 *__restrict__ base,
+                 u64 *status, u32 *ticket, u32 *err)
+{
+    typedef PassSmem<KeyT, ValT, THREADS, IPT> Smem;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * IPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < WARPS * kRadixSize; i += THREADS) sm.whist[i] = 0;
+    __syncthreads();
+    const u32 tile = sm.tile;
+    const u64 tile_base = (u64)tile * TILE;
+    const u32 count = (u32)((n - tile_base) < (u64)TILE ? (n - tile_base) : (u64)TILE);
+
+    // ---- load keys, warp-striped (element order inside the tile = (warp, item, lane))
+    KeyT key[IPT];
+    const u32 wbase = warp * (IPT * 32) + lane;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        u32 li = wbase + i * 32;
+        key[i] = li < count ? kin[tile_base + li] : (KeyT)0;
+    }
+
+    // ---- warp-level multisplit: rank of every item among the items of its warp with the same digit
+    u32 rnk[IPT];
+    u32 *wh = sm.whist + warp * kRadixSize;
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        u32 li = wbase + i * 32;
+        bool valid = li < count;
+        u32 d = valid ? digit_of(key[i], shift, dmask) : (u32)kRadixSize;
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        u32 old = 0;
+        if (lane == leader && valid) { old = wh[d]; wh[d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rnk[i] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive scan over the warps, tile count, chained scan over tiles
+    u32 cnt = 0;
+    if (tid < kRadixSize) {
+        u32 sum = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { u32 t = sm.whist[w * kRadixSize + tid]; sm.whist[w * kRadixSize + tid] = sum; sum += t; }
+        cnt = sum;
+        u64 *mine = status + (u64)tile * kRadixSize + tid;
+        st_relaxed(mine, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
+    }
+    // exclusive scan of the 256 tile counts (threads 0..255 = warps 0..7)
+    {
+        u32 x = cnt;                                   // threads >= 256 carry 0
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+        if (lane == 31) sm.scan_tmp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            u32 v = lane < WARPS ? sm.scan_tmp[lane] : 0;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += y; }
+            sm.scan_tmp[lane] = v;                     // inclusive over warps
+        }
+        __syncthreads();
+        u32 warp_excl = warp ? sm.scan_tmp[warp - 1] : 0;
+        if (tid < kRadixSize) sm.tileoff[tid] = warp_excl + x - cnt;
+    }
+    if (tid < kRadixSize) {
+        u64 excl = 0;
+        if (tile != 0) {
+            u64 *mine = status + (u64)tile * kRadixSize + tid;
+            i64 look = (i64)tile - 1;
+            u32 spins = 0;
+            while (true) {
+                u64 w = ld_relaxed(status + (u64)look * kRadixSize + tid);
+                u64 flag = w >> 62;
+                if (flag == 0) {
+                    if (++spins > kSpinLimit) { *err = 1; break; }
+                    __nanosleep(32);
+                    continue;
+                }
+                excl += w & kStValMask;
+                if (flag == 2 || look == 0) break;
+                --look;
+            }
+            st_relaxed(mine, kStFlagInc | (excl + (u64)cnt));
+        }
+        sm.goff[tid] = base[tid] + excl - (u64)sm.tileoff[tid];
+    }
+    __syncthreads();
+
+    // ---- scatter keys and values into their place inside the tile (shared memory)
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        u32 li = wbase + i * 32;
+        if (li < count) {
+            u32 d = digit_of(key[i], shift, dmask);
+            u32 pos = sm.tileoff[d] + wh[d] + rnk[i];
+            sm.keys[pos] = key[i];
+            rnk[i] = pos;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        u32 li = wbase + i * 32;
+        if (li < count) sm.vals[rnk[i]] = vin[tile_base + li];
+    }
+    __syncthreads();
+
+    // ---- write out: consecutive threads own consecutive slots of a digit's run
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        u32 idx = i * THREADS + tid;
+        if (idx < count) {
+            KeyT k = sm.keys[idx];
+            u64 g = sm.goff[digit_of(k, shift, dmask)] + idx;
+            kout[g] = k;
+            vout[g] = sm.vals[idx];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host driver
+// ---------------------------------------------------------------------------------------------
+template <typename KeyT, typename ValT>
+struct RadixSort {
+    static const int THREADS = 256;
+    static const int IPT = 16;
+    static const int TILE = THREADS * IPT;
+    static const int HIST_THREADS = 512;
+
+    static u64 tiles(u64 n) { return ceil_div(n, TILE); }
+
+    static size_t temp_bytes(u64 n)
+    {
+        return 2 * kMaxPasses * kRadixSize * sizeof(u64)      // hist + base
+             + 256                                            // tickets (u32[kMaxPasses]) + err
+             + tiles(n) * kRadixSize * sizeof(u64);           // status of one pass
+    }
+
+    // Sort n pairs on key bits [lo_bit, hi_bit).  Input in (ka, va); (kb, vb) is the alternate
+    // buffer.  Returns 0 when the result is in (ka, va), 1 when in (kb, vb), -1 on error.
+    // bytes_per_elem_in_algo: sizeof(KeyT)+sizeof(ValT).
+    static int sort(Ctx &c, KeyT *ka, ValT *va, KeyT *kb, ValT *vb, u64 n, int lo_bit, int hi_bit,
+                    void *temp, u32 *err, int *passes_out = nullptr)
+    {
+        SortPlan plan = make_sort_plan(lo_bit, hi_bit);
+        if (passes_out) *passes_out = plan.passes;
+        if (n == 0 || plan.passes == 0) return 0;
+        char *t = (char *)temp;
+        u64 *hist = (u64 *)t;               t += kMaxPasses * kRadixSize * sizeof(u64);
+        u64 *base = (u64 *)t;               t += kMaxPasses * kRadixSize * sizeof(u64);
+        u32 *tickets = (u32 *)t;            t += 256;
+        u64 *status = (u64 *)t;
+        const u64 nt = tiles(n);
+
+        c.check(cudaMemsetAsync(hist, 0, 2 * kMaxPasses * kRadixSize * sizeof(u64) + 256, c.stream));
+        {
+            u64 want = ceil_div(n, (u64)HIST_THREADS * 8);
+            u32 grid = (u32)(want < (u64)c.sm_count * 4 ? (want ? want : 1) : (u64)c.sm_count * 4);
+            LSC_LAUNCH(c, KC_SORT_HIST, (double)n * sizeof(KeyT), (sort_hist_kernel<KeyT, HIST_THREADS>),
+                       grid, HIST_THREADS, 0, ka, n, plan, hist);
+        }
+        LSC_LAUNCH(c, KC_SORT_SCAN, 0.0, sort_scan_kernel, plan.passes, kRadixSize, 0, hist, base);
+
+        typedef PassSmem<KeyT, ValT, THREADS, IPT> Smem;
+        // per device, cheap: opt in to > 48 KB of dynamic shared memory
+        c.check(cudaFuncSetAttribute((sort_pass_kernel<KeyT, ValT, THREADS, IPT>),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        KeyT *kin = ka, *kout = kb; ValT *vin = va, *vout = vb;
+        int where = 0;
+        for (int p = 0; p < plan.passes; ++p) {
+            c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * sizeof(u64), c.stream));
+            LSC_LAUNCH(c, KC_SORT_PASS, 2.0 * (double)n * (sizeof(KeyT) + sizeof(ValT)),
+                       (sort_pass_kernel<KeyT, ValT, THREADS, IPT>), (u32)nt, THREADS, sizeof(Smem),
+                       kin, vin, kout, vout, n, plan.shift[p], (1u << plan.nbits[p]) - 1,
+                       base + p * kRadixSize, status, tickets + p, err);
+            KeyT *tk = kin; kin = kout; kout = tk;
+            ValT *tv = vin; vin = vout; vout = tv;
+            where ^= 1;
+        }
+        return c.failed() ? -1 : where;
+    }
+};
+
+}  // namespace lsc

@@ -1,0 +1,425 @@
+// sa_core.cu -- suffix array + inverse suffix array of a device-resident text by prefix
+// doubling with discarding.  This is the B200-native replacement of the reference's SA-IS
+// core (reference src/libsais.c:6879-6923 libsais_main_8u and :6668-6877
+// libsais_main_32s_recursion); it computes the same, unique, SA.
+//
+// Pipeline:
+//   hist_sym      byte histogram (freq[], alphabet map)                      [~ :1398-1427]
+//   pack          symbols -> order-preserving b-bit codes, big-endian bitstream
+//   make_keys     key(p) = first k codes of suffix p (K = k*b <= 64 bits), in DESCENDING p
+//   onesweep      stable LSD radix sort of (key, p)                          radix_sort.cuh
+//   rank<ROUND0>  head flags, rank = slot of group head, SA/ISA scatter, compaction of the
+//                 suffixes whose group is not yet a singleton ("active")
+//   repeat while active: round_keys (g, ISA[p+h]+1) -> onesweep -> rank<false>; h doubles
+//
+// End-of-text rule ("a suffix that is a prefix of another sorts first", reference
+// include/libsais.h:76-84): keys are zero padded, the initial sort is stable over elements
+// laid out in descending position, and the < k suffixes that run past the end are forced to
+// be singleton groups -- so a short suffix precedes every longer suffix sharing its padded
+// key, exactly as an implicit smallest sentinel would order them.
+#include "core.h"
+#include "radix_sort.cuh"
+#include <cmath>
+#include <cstdlib>
+
+namespace lsc {
+
+// ---------------------------------------------------------------------------------------------
+// symbol statistics
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+byte_hist_kernel(const u8 *__restrict__ T, u64 n, u64 *__restrict__ freq)
+{
+    __shared__ u32 sh[8][256];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    // body: 16 bytes per thread per step (T from cudaMalloc / arena: 16-B aligned), tail: bytes
+    const u64 nvec = ((uintptr_t)T & 15) == 0 ? n / 16 : 0;
+    const uint4 *T4 = reinterpret_cast<const uint4 *>(T);
+    for (u64 v = (u64)blockIdx.x * 256 + tid; v < nvec; v += (u64)gridDim.x * 256) {
+        uint4 q = T4[v];
+        u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sh[warp][w[j] & 255], 1u);
+            atomicAdd(&sh[warp][(w[j] >> 8) & 255], 1u);
+            atomicAdd(&sh[warp][(w[j] >> 16) & 255], 1u);
+            atomicAdd(&sh[warp][w[j] >> 24], 1u);
+        }
+    }
+    for (u64 i = nvec * 16 + (u64)blockIdx.x * 256 + tid; i < n; i += (u64)gridDim.x * 256)
+        atomicAdd(&sh[warp][T[i]], 1u);
+    __syncthreads();
+    u32 s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w][tid];
+    if (s) atomicAdd((unsigned long long *)&freq[tid], (unsigned long long)s);
+}
+
+void run_byte_histogram(Ctx &c, const u8 *d_T, u64 n)
+{
+    c.check(cudaMemsetAsync(c.d_scalars + S_FREQ, 0, 256 * sizeof(u64), c.stream));
+    if (n == 0) return;
+    u64 want = ceil_div(n, 256 * 64);
+    u32 grid = (u32)(want < (u64)c.sm_count * 8 ? want : (u64)c.sm_count * 8);
+    LSC_LAUNCH(c, KC_HIST_SYM, (double)n, byte_hist_kernel, grid, 256, 0, d_T, n, c.d_scalars + S_FREQ);
+}
+
+template <typename SymT>
+__global__ void __launch_bounds__(256)
+max_sym_kernel(const SymT *__restrict__ T, u64 n, u64 *__restrict__ out)
+{
+    u64 m = 0;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+        u64 v = (u64)T[i];
+        m = v > m ? v : m;
+    }
+    for (int off = 16; off; off >>= 1) { u64 o = __shfl_xor_sync(0xffffffffu, m, off); m = o > m ? o : m; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax((unsigned long long *)out, (unsigned long long)m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: word j of the stream holds bits [64j, 64j+64); symbol s occupies bits [s*b, s*b+b),
+// most significant bit first, so a 64-bit window at bit p*b is the big-endian k-mer of suffix p.
+// ---------------------------------------------------------------------------------------------
+template <typename SymT, bool USE_LUT>
+__global__ void __launch_bounds__(256)
+pack_kernel(const SymT *__restrict__ T, u64 n, int b, u64 *__restrict__ words, u64 nwords,
+            const u8 *__restrict__ lut)
+{
+    u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= nwords) return;
+    const u64 bit0 = j * 64;
+    u64 w = 0;
+    for (u64 s = bit0 / (u64)b;; ++s) {
+        u64 sb = s * (u64)b;
+        if (sb >= bit0 + 64) break;
+        u64 code = 0;
+        if (s < n) code = USE_LUT ? (u64)lut[(u32)T[s] & 255] : (u64)T[s];
+        i64 sh = (i64)(bit0 + 64) - (i64)(sb + (u64)b);
+        w |= sh >= 0 ? (code << sh) : (code >> (-sh));
+    }
+    words[j] = w;
+}
+
+// element i <-> position p = n-1-i (descending positions: see the end-of-text rule above)
+__global__ void __launch_bounds__(256)
+make_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int K,
+                 u64 *__restrict__ keys, u32 *__restrict__ pos)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    u64 p = n - 1 - i;
+    u64 bit = p * (u64)b;
+    u64 q = bit >> 6; int off = (int)(bit & 63);
+    u64 hi = words[q], lo = words[q + 1];
+    u64 x = off ? ((hi << off) | (lo >> (64 - off))) : hi;
+    keys[i] = x >> (64 - K);
+    pos[i] = (u32)p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank kernel: sorted (key, pos) -> head flags, rank (= slot of the group head), SA / ISA
+// scatter, compaction of non-singleton ("active") suffixes with their slot and dense group id.
+// One chained scan (decoupled look-back) over tiles for three quantities:
+//   [0] max : slot of the last group head        [1] sum : active suffixes    [2] sum : active groups
+// ---------------------------------------------------------------------------------------------
+static const int kRankThreads = 256;
+static const int kRankIPT = 8;
+static const int kRankTile = kRankThreads * kRankIPT;
+
+__device__ __forceinline__ u64 chained_scan(u64 *status, u32 tile, u64 agg, bool is_max, u32 *err)
+{
+    u64 excl = 0;
+    if (tile == 0) { st_relaxed(status, kStFlagInc | agg); return 0; }
+    st_relaxed(status + tile, kStFlagAgg | agg);
+    i64 look = (i64)tile - 1;
+    u32 spins = 0;
+    while (true) {
+        u64 w = ld_relaxed(status + look);
+        u64 flag = w >> 62;
+        if (flag == 0) {
+            if (++spins > kSpinLimit) { *err = 1; break; }
+            __nanosleep(32);
+            continue;
+        }
+        u64 v = w & kStValMask;
+        excl = is_max ? (v > excl ? v : excl) : excl + v;
+        if (flag == 2 || look == 0) break;
+        --look;
+    }
+    u64 inc = is_max ? (agg > excl ? agg : excl) : excl + agg;
+    st_relaxed(status + tile, kStFlagInc | inc);
+    return excl;
+}
+
+template <bool ROUND0>
+__global__ void __launch_bounds__(kRankThreads)
+rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ slot_in,
+            u64 N, u64 tail_start,
+            u32 *__restrict__ SA, u32 *__restrict__ ISA,
+            u32 *__restrict__ a_pos, u32 *__restrict__ a_slot, u32 *__restrict__ a_grp,
+            u64 *status, u64 ntiles, u32 *ticket, u64 *out_counts, u32 *err)
+{
+    constexpr int WARPS = kRankThreads / 32;
+    __shared__ u32 s_tile;
+    __shared__ u64 s_wagg[3][WARPS];     // per-warp aggregates, then exclusive prefixes (incl. tile prefix)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 tile_base = (u64)tile * kRankTile;
+    const u64 wbase = tile_base + (u64)warp * (kRankIPT * 32) + lane;
+    const u32 lt = lanemask_lt(), le = lt | (1u << lane);
+
+    u32 p[kRankIPT], slot[kRankIPT], hm[kRankIPT], am[kRankIPT], gm[kRankIPT];
+    u64 w_head = 0; u32 w_act = 0, w_grp = 0;
+#pragma unroll
+    for (int i = 0; i < kRankIPT; ++i) {
+        u64 j = wbase + (u64)i * 32;
+        bool valid = j < N;
+        bool head = false, nexthead = true;
+        p[i] = 0; slot[i] = 0;
+        if (valid) {
+            u64 k = keys[j];
+            p[i] = pos[j];
+            slot[i] = ROUND0 ? (u32)j : slot_in[j];
+            head = (j == 0) || (keys[j - 1] != k);
+            nexthead = (j + 1 == N) || (keys[j + 1] != k);
+            if (ROUND0) {
+                bool tail = (u64)p[i] >= tail_start;
+                head = head || tail || ((u64)pos[j - (j ? 1 : 0)] >= tail_start && j != 0);
+                nexthead = nexthead || tail || (j + 1 < N && (u64)pos[j + 1] >= tail_start);
+            }
+        }
+        bool active = valid && !(head && nexthead);
+        hm[i] = __ballot_sync(0xffffffffu, head);
+        am[i] = __ballot_sync(0xffffffffu, active);
+        gm[i] = __ballot_sync(0xffffffffu, active && head);
+        if (hm[i]) {
+            u32 src = 31 - __clz(hm[i]);
+            w_head = (u64)__shfl_sync(0xffffffffu, slot[i], src);   // slots ascend: the latest head wins
+        }
+        w_act += __popc(am[i]);
+        w_grp += __popc(gm[i]);
+    }
+    if (lane == 0) { s_wagg[0][warp] = w_head; s_wagg[1][warp] = w_act; s_wagg[2][warp] = w_grp; }
+    __syncthreads();
+
+    // lanes 0 of warps 0..2 each scan one quantity over the warps, then over the tiles
+    if (lane == 0 && warp < 3) {
+        const bool is_max = warp == 0;
+        u64 run = 0, ex[WARPS];
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            ex[w] = run;
+            u64 v = s_wagg[warp][w];
+            run = is_max ? (v > run ? v : run) : run + v;
+        }
+        u64 excl = chained_scan(status + (u64)warp * ntiles, tile, run, is_max, err);
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w)
+            s_wagg[warp][w] = is_max ? (ex[w] > excl ? ex[w] : excl) : ex[w] + excl;
+        if (tile + 1 == ntiles && !is_max) out_counts[warp - 1] = excl + run;
+    }
+    __syncthreads();
+
+    u32 c_head = (u32)s_wagg[0][warp];
+    u32 c_act = (u32)s_wagg[1][warp];
+    u32 c_grp = (u32)s_wagg[2][warp];
+#pragma unroll
+    for (int i = 0; i < kRankIPT; ++i) {
+        u64 j = wbase + (u64)i * 32;
+        u32 hle = hm[i] & le;
+        u32 src = hle ? (31 - __clz(hle)) : 0;
+        u32 hs = __shfl_sync(0xffffffffu, slot[i], src);
+        u32 rank = hle ? hs : c_head;
+        if (j < N) {
+            SA[slot[i]] = p[i];
+            ISA[p[i]] = rank;
+            if (am[i] & (1u << lane)) {
+                u32 o = c_act + __popc(am[i] & lt);
+                a_pos[o] = p[i];
+                a_slot[o] = slot[i];
+                a_grp[o] = c_grp + __popc(gm[i] & le) - 1;
+            }
+        }
+        if (hm[i]) c_head = __shfl_sync(0xffffffffu, slot[i], 31 - __clz(hm[i]));
+        c_act += __popc(am[i]);
+        c_grp += __popc(gm[i]);
+    }
+}
+
+// round >= 1 keys: (dense group id, rank of the suffix h positions further + 1)
+__global__ void __launch_bounds__(256)
+round_keys_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp,
+                  const u32 *__restrict__ ISA, u64 N, u64 n, u64 h, int rank_bits,
+                  u64 *__restrict__ keys, u32 *__restrict__ pos)
+{
+    u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    u32 p = a_pos[j];
+    u64 q = (u64)p + h;
+    u64 k2 = q < n ? (u64)ISA[q] + 1 : 0;
+    keys[j] = ((u64)a_grp[j] << rank_bits) | k2;
+    pos[j] = p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+size_t sa_workspace_bytes(u64 n, int sym_bytes)
+{
+    u64 nw = ceil_div(n * 64, 64) + 4;                       // worst-case bitstream words (b <= 64)
+    if (sym_bytes == 1) nw = ceil_div(n * 8, 64) + 4;
+    else if (sym_bytes == 4) nw = ceil_div(n * 32, 64) + 4;
+    size_t per = (size_t)n * (8 + 8 + 4 + 4      /* keys, vals (ping-pong) */
+                              + 4 + 4            /* SA, ISA */
+                              + 4 + 4 + 4 + 4);  /* a_pos, a_grp, a_slot x2 */
+    size_t st = 3 * ceil_div(n, kRankTile) * sizeof(u64);
+    return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + 256 + 16 * 256 + 4096;
+}
+
+static int choose_key_symbols(u64 n, int b, double entropy_bits)
+{
+    int kmax = 64 / b;
+    if (kmax < 1) kmax = 1;
+    const char *env = getenv("LIBSAIS_CUDA_KEY_SYMBOLS");
+    if (env && *env) { int k = atoi(env); if (k >= 1) return k < kmax ? k : kmax; }
+    // enough symbols that an iid source of this entropy leaves ~2^-10 of the suffixes tied
+    double need = std::log2((double)(n < 2 ? 2 : n)) + 10.0;
+    if (entropy_bits < 0.05) entropy_bits = 0.05;
+    double kk = std::ceil(need / entropy_bits);
+    int k = kk > (double)kmax ? kmax : (int)kk;
+    if (k < 1) k = 1;
+    // round the key up to whole digit passes: extra symbols are free inside a pass
+    int passes = (k * b + kRadixBits - 1) / kRadixBits;
+    int k2 = (passes * kRadixBits) / b;
+    if (k2 > kmax) k2 = kmax;
+    return k2 > k ? k2 : k;
+}
+
+int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResult *out)
+{
+    if (n == 0) return 0;
+    if (n > kMaxN) return -2;
+    cudaStream_t st = c.stream;
+
+    // ---- alphabet: bits per symbol, order-preserving code map (bytes), key width
+    int b = 8; double entropy = 8.0;
+    u8 *d_lut = nullptr;
+    if (sym_bytes == 1) {
+        run_byte_histogram(c, (const u8 *)d_T, n);
+        c.check(cudaMemcpyAsync(c.h_scalars + S_FREQ, c.d_scalars + S_FREQ, 256 * sizeof(u64),
+                                cudaMemcpyDeviceToHost, st));
+        if (!c.sync()) return -2;
+        u8 lut[256]; int sigma = 0; entropy = 0;
+        for (int s = 0; s < 256; ++s) {
+            u64 f = c.h_scalars[S_FREQ + s];
+            lut[s] = (u8)(sigma ? sigma : 0);
+            if (f) { lut[s] = (u8)sigma; ++sigma; double pr = (double)f / (double)n; entropy -= pr * std::log2(pr); }
+        }
+        b = bits_for((u64)(sigma > 1 ? sigma - 1 : 1));
+        d_lut = c.alloc_n<u8>(256);
+        if (!d_lut) return -2;
+        // h_scalars tail as pinned staging for the LUT
+        u8 *h_lut = (u8 *)(c.h_scalars + S_MISC);
+        for (int s = 0; s < 256; ++s) h_lut[s] = lut[s];
+        c.check(cudaMemcpyAsync(d_lut, h_lut, 256, cudaMemcpyHostToDevice, st));
+    } else {
+        c.check(cudaMemsetAsync(c.d_scalars + S_MAXSYM, 0, sizeof(u64), st));
+        u32 grid = (u32)(ceil_div(n, 256 * 16) < (u64)c.sm_count * 8 ? ceil_div(n, 256 * 16) : (u64)c.sm_count * 8);
+        if (sym_bytes == 4) LSC_LAUNCH(c, KC_HIST_SYM, (double)n * 4, max_sym_kernel<u32>, grid, 256, 0, (const u32 *)d_T, n, c.d_scalars + S_MAXSYM);
+        else                LSC_LAUNCH(c, KC_HIST_SYM, (double)n * 8, max_sym_kernel<u64>, grid, 256, 0, (const u64 *)d_T, n, c.d_scalars + S_MAXSYM);
+        c.check(cudaMemcpyAsync(c.h_scalars + S_MAXSYM, c.d_scalars + S_MAXSYM, sizeof(u64), cudaMemcpyDeviceToHost, st));
+        if (!c.sync()) return -2;
+        b = bits_for(c.h_scalars[S_MAXSYM]);
+        entropy = (double)b;            // unknown distribution: assume dense
+    }
+    const int k = choose_key_symbols(n, b, entropy);
+    const int K = k * b;
+
+    // ---- arena
+    const u64 nwords = ceil_div(n * (u64)b, 64) + 2;
+    u64 *words = c.alloc_n<u64>(nwords);
+    u64 *keyA = c.alloc_n<u64>(n), *keyB = c.alloc_n<u64>(n);
+    u32 *valA = c.alloc_n<u32>(n), *valB = c.alloc_n<u32>(n);
+    u32 *SA = sa_out ? sa_out : c.alloc_n<u32>(n), *ISA = c.alloc_n<u32>(n);
+    u32 *a_pos = c.alloc_n<u32>(n), *a_grp = c.alloc_n<u32>(n);
+    u32 *a_slot0 = c.alloc_n<u32>(n), *a_slot1 = c.alloc_n<u32>(n);
+    const u64 rank_tiles = ceil_div(n, kRankTile);
+    u64 *rstatus = c.alloc_n<u64>(3 * rank_tiles);
+    void *sort_temp = c.alloc(RadixSort<u64, u32>::temp_bytes(n));
+    if (!sort_temp || !rstatus || !a_slot1) return -2;
+    u32 *err = (u32 *)(c.d_scalars + S_ERR);
+    u32 *tickets = (u32 *)(c.d_scalars + S_TICKET);
+    c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, (S_MISC - S_ERR) * sizeof(u64), st));
+
+    // ---- pack + initial keys
+    {
+        u32 grid = (u32)ceil_div(nwords, 256);
+        double ab = (double)n * sym_bytes + (double)nwords * 8;
+        if (sym_bytes == 1) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u8, true>), grid, 256, 0, (const u8 *)d_T, n, b, words, nwords, d_lut);
+        else if (sym_bytes == 4) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u32, false>), grid, 256, 0, (const u32 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
+        else LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u64, false>), grid, 256, 0, (const u64 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
+        LSC_LAUNCH(c, KC_MAKE_KEYS, (double)nwords * 8 + (double)n * 12, make_keys_kernel,
+                   (u32)ceil_div(n, 256), 256, 0, words, n, b, K, keyA, valA);
+    }
+
+    // ---- round 0: sort by the k-mer, rank, compact
+    RoundStat rs; rs.h = 0; rs.n_active = n; rs.key_bits = K; rs.passes = 0; rs.n_groups = 0;
+    int where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, n, 0, K, sort_temp, err, &rs.passes);
+    if (where < 0) return -2;
+    u64 *ks = where ? keyB : keyA; u32 *vs = where ? valB : valA;
+    u64 *ko = where ? keyA : keyB; u32 *vo = where ? valA : valB;
+    u32 *slot_cur = a_slot0, *slot_nxt = a_slot1;
+    {
+        c.check(cudaMemsetAsync(rstatus, 0, 3 * rank_tiles * sizeof(u64), st));
+        const u64 tail_start = n >= (u64)k ? n - (u64)k + 1 : 0;
+        LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + 8), rank_kernel<true>, (u32)rank_tiles, kRankThreads, 0,
+                   ks, vs, (const u32 *)nullptr, n, tail_start, SA, ISA, a_pos, slot_cur, a_grp,
+                   rstatus, rank_tiles, tickets + 0, c.d_scalars + S_NACT, err);
+    }
+    c.check(cudaMemcpyAsync(c.h_scalars + S_ERR, c.d_scalars + S_ERR, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (!c.sync()) return -2;
+    if (c.h_scalars[S_ERR] != 0) { c.last_error = cudaErrorLaunchTimeout; return -2; }
+    u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
+    rs.n_groups = G;
+    c.rounds.push_back(rs);
+
+    // ---- doubling rounds on the active suffixes
+    const int rank_bits = bits_for(n);                 // k2 = ISA+1 <= n
+    u64 h = (u64)k;
+    int round = 1;
+    while (N > 0) {
+        if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
+        const int grp_bits = bits_for(G > 1 ? G - 1 : 1);
+        RoundStat r; r.h = h; r.n_active = N; r.key_bits = rank_bits + grp_bits; r.passes = 0; r.n_groups = 0;
+        // keys go to the pair not holding anything live (everything in ks/vs is dead by now)
+        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel, (u32)ceil_div(N, 256), 256, 0,
+                   a_pos, a_grp, ISA, N, n, h, rank_bits, ks, vs);
+        where = RadixSort<u64, u32>::sort(c, ks, vs, ko, vo, N, 0, rank_bits + grp_bits, sort_temp, err, &r.passes);
+        if (where < 0) return -2;
+        const u64 *sk = where ? ko : ks; const u32 *sv = where ? vo : vs;
+        const u64 tiles = ceil_div(N, kRankTile);
+        c.check(cudaMemsetAsync(rstatus, 0, 3 * rank_tiles * sizeof(u64), st));
+        c.check(cudaMemsetAsync(tickets + (round & 7), 0, sizeof(u32), st));
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 8), rank_kernel<false>, (u32)tiles, kRankThreads, 0,
+                   sk, sv, slot_cur, N, (u64)0, SA, ISA, a_pos, slot_nxt, a_grp,
+                   rstatus, tiles, tickets + (round & 7), c.d_scalars + S_NACT, err);
+        c.check(cudaMemcpyAsync(c.h_scalars + S_ERR, c.d_scalars + S_ERR, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        if (!c.sync()) return -2;
+        if (c.h_scalars[S_ERR] != 0) { c.last_error = cudaErrorLaunchTimeout; return -2; }
+        N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
+        r.n_groups = G;
+        c.rounds.push_back(r);
+        u32 *t = slot_cur; slot_cur = slot_nxt; slot_nxt = t;
+        h *= 2;
+        ++round;
+    }
+    out->SA = SA; out->ISA = ISA; out->scratch = keyA; out->scratch_bytes = (size_t)n * 8;
+    return c.failed() ? -2 : 0;
+}
+
+}  // namespace lsc

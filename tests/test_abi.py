@@ -1,0 +1,90 @@
+"""CPU tests of the drop-in boundary: libsais_cuda.so builds, loads, exports every symbol the
+headers declare, and mirrors the reference's argument validation and n <= 1 fast paths -- none
+of which needs a GPU.  Computing calls must fail loudly (-2) when no CUDA device exists."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _libs
+import checks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import libsais_b200
+    return libsais_b200.device_count() > 0
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import libsais_b200
+    lib = libsais_b200.load_library()
+    with open(os.path.join(ROOT, "tests", "golden", "api_symbols.json")) as f:
+        table = json.load(f)
+    declared = []
+    for hdr in ("libsais.h", "libsais64.h", "libsais_cuda.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)          # declarations only, no comments
+        declared += re.findall(r"\b(libsais\w*)\s*\(", text)
+    declared = sorted(set(declared))
+    # the headers declare exactly the reference's interface (34 + 20 symbols) plus the extras
+    assert set(table["libsais.h"]) <= set(declared) and len(table["libsais.h"]) == 34
+    assert set(table["libsais64.h"]) <= set(declared) and len(table["libsais64.h"]) == 20
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert missing == []
+
+
+def test_only_api_symbols_are_exported():
+    import libsais_b200
+    libsais_b200.load_library()
+    out = subprocess.run(["nm", "-D", "--defined-only", libsais_b200.LIB_PATH], capture_output=True, text=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if l.strip()]
+    assert names and all(n.startswith("libsais") for n in names), [n for n in names if not n.startswith("libsais")][:5]
+
+
+def test_headers_compile_as_c99_and_cxx():
+    src = '#include "libsais.h"\n#include "libsais64.h"\n#include "libsais_cuda.h"\nint main(void){return 0;}\n'
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        r = subprocess.run([cc, std, "-DLIBSAIS_OPENMP", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                            "-x", "c" if cc == "gcc" else "c++", "-"], input=src, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_argument_validation_and_fast_paths():
+    checks.check_errors(_libs.cuda())
+
+
+def test_gsa_entry_points_link_and_report_unsupported():
+    lib = _libs.cuda().lib
+    T = np.frombuffer(b"ab\0ab\0b\0", dtype=np.uint8).copy()
+    SA = np.zeros(8, dtype=np.int32)
+    lib.libsais_gsa.restype = C.c_int32
+    assert lib.libsais_gsa(_libs.ptr(T), _libs.ptr(SA), C.c_int32(8), C.c_int32(0), None) == -1
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product never computes on the CPU: with no CUDA device the call fails with -2."""
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    import libsais_b200
+    rc, SA = _libs.cuda().sa(np.frombuffer(b"banana", dtype=np.uint8).copy())
+    assert rc == -2
+    with pytest.raises(RuntimeError):
+        libsais_b200.Context(0)
+
+
+def test_product_does_not_reference_the_oracle():
+    """Nothing under libsais_b200/ may import, link or open oracle/."""
+    pkg = os.path.join(ROOT, "libsais_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".map")):
+                text = open(os.path.join(dp, f)).read()
+                assert "liboracle" not in text and "oracle/" not in text and "_ref" not in text, os.path.join(dp, f)
+    out = subprocess.run(["ldd", os.path.join(pkg, "libsais_cuda.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libsais_ref" not in out
