@@ -135,8 +135,8 @@ IDX sa_body(Ctx *c, const uint8_t *T, IDX *SA, IDX n, IDX fs, IDX *freq)
     const u8 *d_T = (const u8 *)upload_text(*c, T, (size_t)n);
     if (!d_T) return -2;
     call.start_timer();
-    SAResult res;
-    if (build_sa(*c, d_T, 1, (u64)n, nullptr, &res) != 0) return -2;
+    SAResult res; SAOptions opt;
+    if (build_sa(*c, d_T, 1, (u64)n, opt, &res) != 0) return -2;
     call.stop_timer();
     download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
     if (!call.finish()) return -2;
@@ -157,8 +157,8 @@ IDX sa_int_body(Ctx *c, SYM *T, IDX *SA, IDX n, IDX k, IDX fs)
     const void *d_T = upload_text(*c, T, tb);
     if (!d_T) return -2;
     call.start_timer();
-    SAResult res;
-    if (build_sa(*c, d_T, (int)sizeof(SYM), (u64)n, nullptr, &res) != 0) return -2;
+    SAResult res; SAOptions opt;
+    if (build_sa(*c, d_T, (int)sizeof(SYM), (u64)n, opt, &res) != 0) return -2;
     call.stop_timer();
     download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
     if (!call.finish()) return -2;
@@ -180,23 +180,24 @@ IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *f
     if (!c || !c->ok || (u64)n > kMaxN) return -2;
     Call call(*c);
     const u64 n_aux = aux ? ((u64)n - 1) / (u64)r + 1 : 0;
-    if (!c->reserve((size_t)n * 2 + kPad + n_aux * 4 + sa_workspace_bytes((u64)n, 1) + 8192)) return -2;
+    if (!c->reserve((size_t)n * 3 + kPad + n_aux * 4 + sa_workspace_bytes((u64)n, 1) + 8192)) return -2;
     const u8 *d_T = (const u8 *)upload_text(*c, T, (size_t)n);
     u8 *d_U = c->alloc_n<u8>((size_t)n);
+    u8 *d_rows = c->alloc_n<u8>((size_t)n);
     u32 *d_I = n_aux ? c->alloc_n<u32>(n_aux) : nullptr;
-    if (!d_T || !d_U || (n_aux && !d_I)) return -2;
+    if (!d_T || !d_U || !d_rows || (n_aux && !d_I)) return -2;
     call.start_timer();
-    SAResult res;
-    if (build_sa(*c, d_T, 1, (u64)n, nullptr, &res) != 0) return -2;
-    if (run_bwt(*c, d_T, res.SA, res.ISA, d_U, (u64)n, (u64)r, d_I, n_aux) != 0) return -2;
+    SAResult res; SAOptions opt;
+    opt.want_sa = false; opt.bwt_rows = d_rows; opt.aux_r = aux ? (u64)r : 0; opt.aux_I = d_I;
+    if (build_sa(*c, d_T, 1, (u64)n, opt, &res) != 0) return -2;
+    if (res.primary < 1 || res.primary > (u64)n) return -2;
+    if (run_bwt_finish(*c, d_T, d_rows, d_U, (u64)n, res.primary) != 0) return -2;
     call.stop_timer();
     c->check(cudaMemcpyAsync(U, d_U, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    u32 *h_p0 = (u32 *)(c->h_scalars + S_PRIMARY);
-    c->check(cudaMemcpyAsync(h_p0, res.ISA, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
     if (n_aux) download_indexes<IDX>(*c, d_I, I, n_aux, res.scratch);
     if (!call.finish()) return -2;
     store_freq(*c, freq);
-    return aux ? 0 : (IDX)((u64)*h_p0 + 1);
+    return aux ? 0 : (IDX)res.primary;
 }
 
 template <typename IDX>
@@ -426,8 +427,9 @@ int64_t libsais_cuda_sa_dev(const void *ctx, const uint8_t *d_T, uint32_t *d_SA,
     Call call(*c);
     if (!c->reserve(sa_workspace_bytes((u64)n, 1) + 4096)) return -2;
     call.start_timer();
-    SAResult res;
-    if (build_sa(*c, d_T, 1, (u64)n, d_SA, &res) != 0) return -2;
+    SAResult res; SAOptions opt;
+    opt.sa_out = d_SA;
+    if (build_sa(*c, d_T, 1, (u64)n, opt, &res) != 0) return -2;
     call.stop_timer();
     return call.finish() ? 0 : -2;
 }
@@ -439,16 +441,18 @@ int64_t libsais_cuda_bwt_dev(const void *ctx, const uint8_t *d_T, uint8_t *d_U, 
     if (!c || !c->ok || (u64)n > kMaxN) return -2;
     if (n == 0) return 0;
     Call call(*c);
-    if (!c->reserve(sa_workspace_bytes((u64)n, 1) + 4096)) return -2;
+    if (!c->reserve((size_t)n + sa_workspace_bytes((u64)n, 1) + 4096)) return -2;
+    u8 *d_rows = c->alloc_n<u8>((size_t)n);
+    if (!d_rows) return -2;
     call.start_timer();
-    SAResult res;
-    if (build_sa(*c, d_T, 1, (u64)n, nullptr, &res) != 0) return -2;
-    if (run_bwt(*c, d_T, res.SA, res.ISA, d_U, (u64)n, 0, nullptr, 0) != 0) return -2;
+    SAResult res; SAOptions opt;
+    opt.want_sa = false; opt.bwt_rows = d_rows;
+    if (build_sa(*c, d_T, 1, (u64)n, opt, &res) != 0) return -2;
+    if (res.primary < 1 || res.primary > (u64)n) return -2;
+    if (run_bwt_finish(*c, d_T, d_rows, d_U, (u64)n, res.primary) != 0) return -2;
     call.stop_timer();
-    u32 *h_p0 = (u32 *)(c->h_scalars + S_PRIMARY);
-    c->check(cudaMemcpyAsync(h_p0, res.ISA, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
     if (!call.finish()) return -2;
-    return (int64_t)*h_p0 + 1;
+    return (int64_t)res.primary;
 }
 
 int64_t libsais_cuda_plcp_dev(const void *ctx, const uint8_t *d_T, const uint32_t *d_SA, uint32_t *d_PLCP, int64_t n)

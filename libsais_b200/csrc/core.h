@@ -16,9 +16,19 @@ enum ScalarSlot {
     S_MISC    = 272
 };
 
+struct SAOptions {
+    bool want_sa = true;          // materialise SA (false: BWT-only callers never need it)
+    u32 *sa_out = nullptr;        // caller's device buffer for SA instead of an arena array
+    u8 *bwt_rows = nullptr;       // byte texts only: rows[slot] = byte preceding the suffix in that SA slot
+    u64 aux_r = 0;                // aux sampling: aux_I[p / r] = slot(p) + 1 for p % r == 0 (r a power of two)
+    u32 *aux_I = nullptr;
+};
+
 struct SAResult {
-    u32 *SA = nullptr;    // [n]   suffix array
-    u32 *ISA = nullptr;   // [n]   inverse suffix array (rank of every suffix)
+    u32 *SA = nullptr;    // [n]   suffix array (nullptr when !want_sa)
+    u32 *ISA = nullptr;   // [n]   inverse suffix array; complete only when isa_complete
+    bool isa_complete = false;
+    u64 primary = 0;      // slot of suffix 0, plus 1 (= the BWT primary index)
     void *scratch = nullptr;      // dead sort buffer, reusable by the caller after the build
     size_t scratch_bytes = 0;     // = 8n
 };
@@ -29,13 +39,11 @@ size_t sa_workspace_bytes(u64 n, int sym_bytes);
 // Build SA and ISA of a device-resident text.  sym_bytes = 1 (bytes; the histogram is left in
 // ctx.h_scalars[S_FREQ..+256) after the call), 4 (int32 symbols) or 8 (int64 symbols).
 // Returns 0, or -2 on CUDA failure / exhausted workspace.  Arrays live in the ctx arena.
-// sa_out (optional): caller's device buffer for SA instead of an arena array.
-int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResult *out);
+int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt, SAResult *out);
 
 // Post-processing stages (all device pointers).
-//   bwt:   U[n] from T, SA, ISA;  *primary (host) = ISA[0]+1;  aux (device, optional): I[j] = ISA[j*r]+1
-int run_bwt(Ctx &c, const u8 *d_T, const u32 *d_SA, const u32 *d_ISA, u8 *d_U, u64 n,
-            u64 r, u32 *d_I, u64 n_aux);
+//   bwt:   U[n] from the per-slot rows produced by build_sa (SAOptions::bwt_rows) and the primary index
+int run_bwt_finish(Ctx &c, const u8 *d_T, const u8 *d_rows, u8 *d_U, u64 n, u64 primary);
 //   plcp:  PLCP[n] from T (sym_bytes 1 or 4), SA.  d_T must be readable up to 16 bytes past the end.
 int run_plcp(Ctx &c, const void *d_T, int sym_bytes, const u32 *d_SA, u32 *d_PLCP, u64 n);
 //   lcp:   LCP[i] = PLCP[SA[i]]

@@ -7,36 +7,22 @@
 namespace lsc {
 
 // ---------------------------------------------------------------------------------------------
-// BWT gather.  Reference: final_bwt_scan_* + bwt_copy_8u, src/libsais.c:4777-4797, :5396-5422,
-// :6960-7006, assembly :7110-7118.  With p0 = ISA[0]:  U[0] = T[n-1];  slot i != p0 writes
-// T[SA[i]-1] to U[i + (i < p0)].
+// BWT assembly.  Reference: final_bwt_scan_* + bwt_copy_8u, src/libsais.c:4777-4797, :5396-5422,
+// :6960-7006, assembly :7110-7118.  The SA core already produced rows[i] = T[SA[i]-1] for every
+// slot (the byte rides through the sort in the key's low bits); with p0 = primary-1 the slot of
+// suffix 0:  U[0] = T[n-1];  slot i != p0 goes to U[i + (i < p0)]  (the "$" row is dropped).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-bwt_kernel(const u8 *__restrict__ T, const u32 *__restrict__ SA, const u32 *__restrict__ ISA,
-           u8 *__restrict__ U, u64 n)
+bwt_finish_kernel(const u8 *__restrict__ T, const u8 *__restrict__ rows, u8 *__restrict__ U, u64 n, u64 p0)
 {
-    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const u64 p0 = ISA[0];
-    if (i == 0) U[0] = T[n - 1];
-    u32 s = ld_stream(SA + i);
-    if (s != 0) U[i + (i < p0 ? 1 : 0)] = T[s - 1];
+    u64 o = (u64)blockIdx.x * 256 + threadIdx.x;       // output index
+    if (o >= n) return;
+    U[o] = o == 0 ? T[n - 1] : rows[o <= p0 ? o - 1 : o];
 }
 
-// aux indexes: I[j] = ISA[j*r] + 1   (reference :4811, :5286, :5437)
-__global__ void __launch_bounds__(256)
-bwt_aux_kernel(const u32 *__restrict__ ISA, u64 r, u32 *__restrict__ I, u64 n_aux)
+int run_bwt_finish(Ctx &c, const u8 *d_T, const u8 *d_rows, u8 *d_U, u64 n, u64 primary)
 {
-    u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (j < n_aux) I[j] = ISA[j * r] + 1;
-}
-
-int run_bwt(Ctx &c, const u8 *d_T, const u32 *d_SA, const u32 *d_ISA, u8 *d_U, u64 n,
-            u64 r, u32 *d_I, u64 n_aux)
-{
-    LSC_LAUNCH(c, KC_BWT, (double)n * 6, bwt_kernel, (u32)ceil_div(n, 256), 256, 0, d_T, d_SA, d_ISA, d_U, n);
-    if (d_I && n_aux)
-        LSC_LAUNCH(c, KC_BWT, (double)n_aux * 8, bwt_aux_kernel, (u32)ceil_div(n_aux, 256), 256, 0, d_ISA, r, d_I, n_aux);
+    LSC_LAUNCH(c, KC_BWT, (double)n * 2, bwt_finish_kernel, (u32)ceil_div(n, 256), 256, 0, d_T, d_rows, d_U, n, primary - 1);
     return c.failed() ? -2 : 0;
 }
 

@@ -12,6 +12,7 @@
 #pragma once
 #include "common.cuh"
 #include "ctx.h"
+#include <cstdlib>
 
 namespace lsc {
 
@@ -102,29 +103,82 @@ static __global__ void sort_scan_kernel(const u64 *__restrict__ hist, u64 *__res
 
 // ---------------------------------------------------------------------------------------------
 // One digit pass.
+//   VALS : 0 = values loaded late (scatter phase), 1 = loaded early into registers,
+//          2 = prefetched into shared memory with cp.async (no registers, latency overlapped)
+//   EARLY: publish the tile's digit counts before the ranking (counting pre-pass with
+//          shared-memory atomics) so successors' look-back rarely finds an unpublished tile
 // ---------------------------------------------------------------------------------------------
-template <typename KeyT, typename ValT, int THREADS, int IPT>
+template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS>
 struct PassSmem {
     static const int TILE = THREADS * IPT;
     KeyT keys[TILE];
     u64  goff[kRadixSize];                 // global offset of a digit's run minus its offset in the tile
     ValT vals[TILE];
+    ValT vals_in[VALS == 2 ? TILE : 1];
     u32  whist[(THREADS / 32) * kRadixSize];
     u32  tileoff[kRadixSize];
+    u32  early[kRadixSize];
     u32  scan_tmp[32];
     u32  tile;
 };
 
-template <typename KeyT, typename ValT, int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS)
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+    u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+static const int kLookBatch = 8;           // predecessor status words fetched per look-back round trip
+
+// Exclusive prefix of this tile's digit count over all earlier tiles (decoupled look-back).
+// The predecessors' status words are fetched kLookBatch at a time so one L2 round trip
+// covers several tiles; a word that is not published yet is polled individually.
+__device__ __forceinline__ u64 lookback_digit(u64 *status, u32 tile, u32 digit, u32 cnt, u32 *err)
+{
+    u64 *mine = status + (u64)tile * kRadixSize + digit;
+    if (tile == 0) return 0;
+    u64 excl = 0;
+    i64 look = (i64)tile - 1;
+    bool done = false;
+    while (!done) {
+        u64 w[kLookBatch];
+#pragma unroll
+        for (int j = 0; j < kLookBatch; ++j) {
+            i64 idx = look - j;
+            w[j] = idx >= 0 ? ld_relaxed(status + (u64)idx * kRadixSize + digit) : kStFlagInc;
+        }
+#pragma unroll
+        for (int j = 0; j < kLookBatch; ++j) {
+            if (!done) {
+                u64 x = w[j];
+                u32 spins = 0;
+                while ((x >> 62) == 0) {
+                    if (++spins > kSpinLimit) { *err = 1; x = kStFlagInc; break; }
+                    __nanosleep(20);
+                    x = ld_relaxed(status + (u64)(look - j) * kRadixSize + digit);
+                }
+                excl += x & kStValMask;
+                if ((x >> 62) == 2) done = true;
+            }
+        }
+        look -= kLookBatch;
+    }
+    st_relaxed(mine, kStFlagInc | (excl + (u64)cnt));
+    return excl;
+}
+
+template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, bool EARLY>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 2))
 sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
                  KeyT *__restrict__ kout, ValT *__restrict__ vout, u64 n,
                  int shift, u32 dmask, const u64 *__restrict__ base,
                  u64 *status, u32 *ticket, u32 *err)
 {
-    typedef PassSmem<KeyT, ValT, THREADS, IPT> Smem;
+    typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * IPT;
+    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one thread per digit is assumed");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
@@ -132,6 +186,7 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
 
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < WARPS * kRadixSize; i += THREADS) sm.whist[i] = 0;
+    if (EARLY && tid < kRadixSize) sm.early[tid] = 0;
     __syncthreads();
     const u32 tile = sm.tile;
     const u64 tile_base = (u64)tile * TILE;
@@ -139,11 +194,40 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
 
     // ---- load keys, warp-striped (element order inside the tile = (warp, item, lane))
     KeyT key[IPT];
+    ValT val[VALS == 1 ? IPT : 1];
     const u32 wbase = warp * (IPT * 32) + lane;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 li = wbase + i * 32;
         key[i] = li < count ? kin[tile_base + li] : (KeyT)0;
+    }
+    if (VALS == 1) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            u32 li = wbase + i * 32;
+            val[VALS == 1 ? i : 0] = li < count ? vin[tile_base + li] : (ValT)0;
+        }
+    } else if (VALS == 2) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            u32 li = wbase + i * 32;
+            if (li < count) cp_async4(&sm.vals_in[VALS == 2 ? li : 0], vin + tile_base + li);
+        }
+    }
+
+    u32 cnt = 0;
+    if (EARLY) {
+        // counting pre-pass: tile digit counts, published before the (longer) ranking phase
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            u32 li = wbase + i * 32;
+            if (li < count) atomicAdd(&sm.early[digit_of(key[i], shift, dmask)], 1u);
+        }
+        __syncthreads();
+        if (tid < kRadixSize) {
+            cnt = sm.early[tid];
+            st_relaxed(status + (u64)tile * kRadixSize + tid, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
+        }
     }
 
     // ---- warp-level multisplit: rank of every item among the items of its warp with the same digit
@@ -165,19 +249,19 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     }
     __syncthreads();
 
-    // ---- per digit: exclusive scan over the warps, tile count, chained scan over tiles
-    u32 cnt = 0;
+    // ---- per digit: exclusive scan over the warps, tile count
     if (tid < kRadixSize) {
         u32 sum = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) { u32 t = sm.whist[w * kRadixSize + tid]; sm.whist[w * kRadixSize + tid] = sum; sum += t; }
-        cnt = sum;
-        u64 *mine = status + (u64)tile * kRadixSize + tid;
-        st_relaxed(mine, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
+        if (!EARLY) {
+            cnt = sum;
+            st_relaxed(status + (u64)tile * kRadixSize + tid, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
+        }
     }
-    // exclusive scan of the 256 tile counts (threads 0..255 = warps 0..7)
+    // exclusive scan of the 256 tile counts (threads >= 256 carry 0)
     {
-        u32 x = cnt;                                   // threads >= 256 carry 0
+        u32 x = cnt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
         if (lane == 31) sm.scan_tmp[warp] = x;
@@ -192,28 +276,12 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
         u32 warp_excl = warp ? sm.scan_tmp[warp - 1] : 0;
         if (tid < kRadixSize) sm.tileoff[tid] = warp_excl + x - cnt;
     }
+    // ---- chained scan over tiles
     if (tid < kRadixSize) {
-        u64 excl = 0;
-        if (tile != 0) {
-            u64 *mine = status + (u64)tile * kRadixSize + tid;
-            i64 look = (i64)tile - 1;
-            u32 spins = 0;
-            while (true) {
-                u64 w = ld_relaxed(status + (u64)look * kRadixSize + tid);
-                u64 flag = w >> 62;
-                if (flag == 0) {
-                    if (++spins > kSpinLimit) { *err = 1; break; }
-                    __nanosleep(32);
-                    continue;
-                }
-                excl += w & kStValMask;
-                if (flag == 2 || look == 0) break;
-                --look;
-            }
-            st_relaxed(mine, kStFlagInc | (excl + (u64)cnt));
-        }
+        u64 excl = lookback_digit(status, tile, (u32)tid, cnt, err);
         sm.goff[tid] = base[tid] + excl - (u64)sm.tileoff[tid];
     }
+    if (VALS == 2) cp_async_wait_all();
     __syncthreads();
 
     // ---- scatter keys and values into their place inside the tile (shared memory)
@@ -224,13 +292,17 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
             u32 d = digit_of(key[i], shift, dmask);
             u32 pos = sm.tileoff[d] + wh[d] + rnk[i];
             sm.keys[pos] = key[i];
-            rnk[i] = pos;
+            if (VALS == 1) sm.vals[pos] = val[VALS == 1 ? i : 0];
+            else if (VALS == 2) sm.vals[pos] = sm.vals_in[VALS == 2 ? li : 0];
+            else rnk[i] = pos;
         }
     }
+    if (VALS == 0) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        u32 li = wbase + i * 32;
-        if (li < count) sm.vals[rnk[i]] = vin[tile_base + li];
+        for (int i = 0; i < IPT; ++i) {
+            u32 li = wbase + i * 32;
+            if (li < count) sm.vals[rnk[i]] = vin[tile_base + li];
+        }
     }
     __syncthreads();
 
@@ -250,25 +322,54 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
 // ---------------------------------------------------------------------------------------------
 // Host driver
 // ---------------------------------------------------------------------------------------------
+// Tuning variants of the pass kernel, selectable with LIBSAIS_CUDA_SORT_VARIANT for experiments.
+struct PassVariant { int threads, ipt, vals, early; };
+static const PassVariant kPassVariants[] = {
+    {256, 16, 0, 0}, {256, 16, 2, 0}, {256, 16, 2, 1}, {512, 8, 1, 0}, {512, 8, 1, 1}, {512, 8, 2, 1},
+    {384, 12, 2, 1}, {256, 16, 0, 1},
+};
+static const int kNumPassVariants = sizeof(kPassVariants) / sizeof(kPassVariants[0]);
+static const int kDefaultPassVariant = 2;
+
+static inline int pass_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LIBSAIS_CUDA_SORT_VARIANT");
+        v = (e && *e) ? atoi(e) : kDefaultPassVariant;
+        if (v < 0 || v >= kNumPassVariants) v = kDefaultPassVariant;
+    }
+    return v;
+}
+
 template <typename KeyT, typename ValT>
 struct RadixSort {
-    static const int THREADS = 256;
-    static const int IPT = 16;
-    static const int TILE = THREADS * IPT;
     static const int HIST_THREADS = 512;
 
-    static u64 tiles(u64 n) { return ceil_div(n, TILE); }
+    static int tile_elems() { const PassVariant &pv = kPassVariants[pass_variant()]; return pv.threads * pv.ipt; }
+    static u64 tiles(u64 n) { return ceil_div(n, (u64)tile_elems()); }
 
     static size_t temp_bytes(u64 n)
     {
         return 2 * kMaxPasses * kRadixSize * sizeof(u64)      // hist + base
-             + 256                                            // tickets (u32[kMaxPasses]) + err
-             + tiles(n) * kRadixSize * sizeof(u64);           // status of one pass
+             + 256                                            // tickets (u32[kMaxPasses])
+             + ceil_div(n, 3072) * kRadixSize * sizeof(u64);  // status of one pass (smallest tile of any variant)
+    }
+
+    template <int THREADS, int IPT, int VALS, bool EARLY>
+    static void launch_pass(Ctx &c, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout, u64 n, int shift, u32 dmask,
+                            const u64 *base, u64 *status, u32 *ticket, u32 *err)
+    {
+        typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
+        auto kern = sort_pass_kernel<KeyT, ValT, THREADS, IPT, VALS, EARLY>;
+        c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        u64 nt = ceil_div(n, (u64)THREADS * IPT);
+        LSC_LAUNCH(c, KC_SORT_PASS, 2.0 * (double)n * (sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
+                   kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err);
     }
 
     // Sort n pairs on key bits [lo_bit, hi_bit).  Input in (ka, va); (kb, vb) is the alternate
     // buffer.  Returns 0 when the result is in (ka, va), 1 when in (kb, vb), -1 on error.
-    // bytes_per_elem_in_algo: sizeof(KeyT)+sizeof(ValT).
     static int sort(Ctx &c, KeyT *ka, ValT *va, KeyT *kb, ValT *vb, u64 n, int lo_bit, int hi_bit,
                     void *temp, u32 *err, int *passes_out = nullptr)
     {
@@ -291,19 +392,24 @@ struct RadixSort {
         }
         LSC_LAUNCH(c, KC_SORT_SCAN, 0.0, sort_scan_kernel, plan.passes, kRadixSize, 0, hist, base);
 
-        typedef PassSmem<KeyT, ValT, THREADS, IPT> Smem;
-        // per device, cheap: opt in to > 48 KB of dynamic shared memory
-        c.check(cudaFuncSetAttribute((sort_pass_kernel<KeyT, ValT, THREADS, IPT>),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         KeyT *kin = ka, *kout = kb; ValT *vin = va, *vout = vb;
         int where = 0;
+        const int variant = pass_variant();
         for (int p = 0; p < plan.passes; ++p) {
             c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * sizeof(u64), c.stream));
-            LSC_LAUNCH(c, KC_SORT_PASS, 2.0 * (double)n * (sizeof(KeyT) + sizeof(ValT)),
-                       (sort_pass_kernel<KeyT, ValT, THREADS, IPT>), (u32)nt, THREADS, sizeof(Smem),
-                       kin, vin, kout, vout, n, plan.shift[p], (1u << plan.nbits[p]) - 1,
-                       base + p * kRadixSize, status, tickets + p, err);
-            KeyT *tk = kin; kin = kout; kout = tk;
+            const int shift = plan.shift[p]; const u32 dmask = (1u << plan.nbits[p]) - 1;
+            const u64 *bp = base + p * kRadixSize; u32 *tk = tickets + p;
+            switch (variant) {
+            case 0: launch_pass<256, 16, 0, false>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            case 1: launch_pass<256, 16, 2, false>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            case 2: launch_pass<256, 16, 2, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            case 3: launch_pass<512, 8, 1, false>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            case 4: launch_pass<512, 8, 1, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            case 5: launch_pass<512, 8, 2, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            case 6: launch_pass<384, 12, 2, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            default: launch_pass<256, 16, 0, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
+            }
+            KeyT *tk2 = kin; kin = kout; kout = tk2;
             ValT *tv = vin; vin = vout; vout = tv;
             where ^= 1;
         }

@@ -103,77 +103,110 @@ pack_kernel(const SymT *__restrict__ T, u64 n, int b, u64 *__restrict__ words, u
     words[j] = w;
 }
 
-// element i <-> position p = n-1-i (descending positions: see the end-of-text rule above)
-__global__ void __launch_bounds__(256)
-make_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int K,
-                 u64 *__restrict__ keys, u32 *__restrict__ pos)
+// k-mer of suffix p: the K most significant bits of the 64-bit window at bit p*b
+__device__ __forceinline__ u64 kmer_at(const u64 *__restrict__ words, u64 p, int b, int K)
 {
-    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    u64 p = n - 1 - i;
     u64 bit = p * (u64)b;
     u64 q = bit >> 6; int off = (int)(bit & 63);
     u64 hi = words[q], lo = words[q + 1];
     u64 x = off ? ((hi << off) | (lo >> (64 - off))) : hi;
-    keys[i] = x >> (64 - K);
+    return x >> (64 - K);
+}
+
+// element i <-> position p = n-1-i (descending positions: see the end-of-text rule above).
+// BWT mode (text != nullptr): the byte preceding the suffix rides in the low 8 key bits,
+// below the sorted bit range, so the BWT falls out of the sort without a gather.
+__global__ void __launch_bounds__(256)
+make_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int K, int key_shift,
+                 const u8 *__restrict__ text, u64 *__restrict__ keys, u32 *__restrict__ pos)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    u64 p = n - 1 - i;
+    u64 key = kmer_at(words, p, b, K) << key_shift;
+    if (text != nullptr && p > 0) key |= (u64)text[p - 1];
+    keys[i] = key;
     pos[i] = (u32)p;
 }
 
 // ---------------------------------------------------------------------------------------------
 // rank kernel: sorted (key, pos) -> head flags, rank (= slot of the group head), SA / ISA
-// scatter, compaction of non-singleton ("active") suffixes with their slot and dense group id.
-// One chained scan (decoupled look-back) over tiles for three quantities:
+// scatter, compaction of non-singleton ("active") suffixes with their slot and dense group id,
+// and -- for suffixes that became singletons ("final") -- the fused outputs: BWT row byte,
+// primary index, aux samples.
+// One chained scan (decoupled look-back, warp-wide window) over tiles for three quantities:
 //   [0] max : slot of the last group head        [1] sum : active suffixes    [2] sum : active groups
 // ---------------------------------------------------------------------------------------------
 static const int kRankThreads = 256;
 static const int kRankIPT = 8;
 static const int kRankTile = kRankThreads * kRankIPT;
+static const u32 kIsaInvalid = 0xFFFFFFFFu;
 
-__device__ __forceinline__ u64 chained_scan(u64 *status, u32 tile, u64 agg, bool is_max, u32 *err)
+struct RankArgs {
+    const u64 *keys; const u32 *pos; const u32 *slot_in;
+    u64 N; u64 tail_start; int key_shift;
+    u32 *SA;                 // nullable: SA[slot] = pos
+    u32 *ISA; int isa_all;   // isa_all: write every element's rank, else only the active ones
+    u8 *rows; const u8 *text;            // BWT mode: rows[slot] = byte preceding the suffix
+    u64 aux_mask; int aux_shift; u32 *aux_I;
+    u64 *primary;
+    u32 *a_pos, *a_slot, *a_grp;
+    u64 *status; u64 ntiles; u32 *ticket; u64 *out_counts; u32 *err;
+};
+
+// Warp-wide chained scan: all 32 lanes call; lane 0's `agg` is the tile aggregate.  Each round
+// trip inspects 32 predecessors.  Returns the exclusive prefix (all lanes).
+__device__ __forceinline__ u64 chained_scan_warp(u64 *status, u32 tile, u64 agg, bool is_max, u32 *err, int lane)
 {
+    agg = __shfl_sync(0xffffffffu, agg, 0);
+    if (tile == 0) { if (lane == 0) st_relaxed(status, kStFlagInc | agg); return 0; }
+    if (lane == 0) st_relaxed(status + tile, kStFlagAgg | agg);
     u64 excl = 0;
-    if (tile == 0) { st_relaxed(status, kStFlagInc | agg); return 0; }
-    st_relaxed(status + tile, kStFlagAgg | agg);
     i64 look = (i64)tile - 1;
-    u32 spins = 0;
     while (true) {
-        u64 w = ld_relaxed(status + look);
-        u64 flag = w >> 62;
-        if (flag == 0) {
-            if (++spins > kSpinLimit) { *err = 1; break; }
-            __nanosleep(32);
-            continue;
+        i64 idx = look - lane;
+        u64 w = kStFlagInc;                       // before the first tile: an inclusive identity
+        u32 spins = 0;
+        while (true) {
+            if (idx >= 0) w = ld_relaxed(status + idx);
+            if (!__any_sync(0xffffffffu, (w >> 62) == 0)) break;
+            if (++spins > kSpinLimit) { *err = 1; w |= kStFlagInc; break; }
+            __nanosleep(20);
         }
-        u64 v = w & kStValMask;
+        u32 incmask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        int first = incmask ? (__ffs(incmask) - 1) : 31;
+        u64 v = lane <= first ? (w & kStValMask) : 0;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            u64 o = __shfl_xor_sync(0xffffffffu, v, off);
+            v = is_max ? (o > v ? o : v) : v + o;
+        }
         excl = is_max ? (v > excl ? v : excl) : excl + v;
-        if (flag == 2 || look == 0) break;
-        --look;
+        if (incmask) break;
+        look -= 32;
     }
-    u64 inc = is_max ? (agg > excl ? agg : excl) : excl + agg;
-    st_relaxed(status + tile, kStFlagInc | inc);
+    if (lane == 0) st_relaxed(status + tile, kStFlagInc | (is_max ? (agg > excl ? agg : excl) : excl + agg));
     return excl;
 }
 
 template <bool ROUND0>
 __global__ void __launch_bounds__(kRankThreads)
-rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ slot_in,
-            u64 N, u64 tail_start,
-            u32 *__restrict__ SA, u32 *__restrict__ ISA,
-            u32 *__restrict__ a_pos, u32 *__restrict__ a_slot, u32 *__restrict__ a_grp,
-            u64 *status, u64 ntiles, u32 *ticket, u64 *out_counts, u32 *err)
+rank_kernel(const RankArgs a)
 {
     constexpr int WARPS = kRankThreads / 32;
     __shared__ u32 s_tile;
     __shared__ u64 s_wagg[3][WARPS];     // per-warp aggregates, then exclusive prefixes (incl. tile prefix)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
     __syncthreads();
     const u32 tile = s_tile;
+    const u64 N = a.N;
     const u64 tile_base = (u64)tile * kRankTile;
     const u64 wbase = tile_base + (u64)warp * (kRankIPT * 32) + lane;
     const u32 lt = lanemask_lt(), le = lt | (1u << lane);
 
     u32 p[kRankIPT], slot[kRankIPT], hm[kRankIPT], am[kRankIPT], gm[kRankIPT];
+    u32 pc[ROUND0 ? kRankIPT / 4 : 1] = {0};
     u64 w_head = 0; u32 w_act = 0, w_grp = 0;
 #pragma unroll
     for (int i = 0; i < kRankIPT; ++i) {
@@ -182,15 +215,17 @@ rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, const u32
         bool head = false, nexthead = true;
         p[i] = 0; slot[i] = 0;
         if (valid) {
-            u64 k = keys[j];
-            p[i] = pos[j];
-            slot[i] = ROUND0 ? (u32)j : slot_in[j];
-            head = (j == 0) || (keys[j - 1] != k);
-            nexthead = (j + 1 == N) || (keys[j + 1] != k);
+            u64 kraw = a.keys[j];
+            u64 k = kraw >> a.key_shift;
+            p[i] = a.pos[j];
+            slot[i] = ROUND0 ? (u32)j : a.slot_in[j];
+            if (ROUND0) pc[i >> 2] |= (u32)(kraw & 255) << (8 * (i & 3));
+            head = (j == 0) || ((a.keys[j - 1] >> a.key_shift) != k);
+            nexthead = (j + 1 == N) || ((a.keys[j + 1] >> a.key_shift) != k);
             if (ROUND0) {
-                bool tail = (u64)p[i] >= tail_start;
-                head = head || tail || ((u64)pos[j - (j ? 1 : 0)] >= tail_start && j != 0);
-                nexthead = nexthead || tail || (j + 1 < N && (u64)pos[j + 1] >= tail_start);
+                bool tail = (u64)p[i] >= a.tail_start;
+                head = head || tail || (j != 0 && (u64)a.pos[j - (j ? 1 : 0)] >= a.tail_start);
+                nexthead = nexthead || tail || (j + 1 < N && (u64)a.pos[j + 1] >= a.tail_start);
             }
         }
         bool active = valid && !(head && nexthead);
@@ -207,21 +242,22 @@ rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, const u32
     if (lane == 0) { s_wagg[0][warp] = w_head; s_wagg[1][warp] = w_act; s_wagg[2][warp] = w_grp; }
     __syncthreads();
 
-    // lanes 0 of warps 0..2 each scan one quantity over the warps, then over the tiles
-    if (lane == 0 && warp < 3) {
+    // warps 0..2 each scan one quantity: over the block's warps (lanes 0..WARPS-1), then over the tiles
+    if (warp < 3) {
         const bool is_max = warp == 0;
-        u64 run = 0, ex[WARPS];
+        u64 mine = lane < WARPS ? s_wagg[warp][lane] : 0;
+        u64 inc = mine;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            ex[w] = run;
-            u64 v = s_wagg[warp][w];
-            run = is_max ? (v > run ? v : run) : run + v;
+        for (int off = 1; off < WARPS; off <<= 1) {
+            u64 o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc = is_max ? (o > inc ? o : inc) : inc + o;
         }
-        u64 excl = chained_scan(status + (u64)warp * ntiles, tile, run, is_max, err);
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w)
-            s_wagg[warp][w] = is_max ? (ex[w] > excl ? ex[w] : excl) : ex[w] + excl;
-        if (tile + 1 == ntiles && !is_max) out_counts[warp - 1] = excl + run;
+        u64 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = 0;
+        u64 total = __shfl_sync(0xffffffffu, inc, WARPS - 1);
+        u64 excl = chained_scan_warp(a.status + (u64)warp * a.ntiles, tile, total, is_max, a.err, lane);
+        if (lane < WARPS) s_wagg[warp][lane] = is_max ? (ex > excl ? ex : excl) : ex + excl;
+        if (tile + 1 == a.ntiles && !is_max && lane == 0) a.out_counts[warp - 1] = excl + total;
     }
     __syncthreads();
 
@@ -236,13 +272,22 @@ rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, const u32
         u32 hs = __shfl_sync(0xffffffffu, slot[i], src);
         u32 rank = hle ? hs : c_head;
         if (j < N) {
-            SA[slot[i]] = p[i];
-            ISA[p[i]] = rank;
-            if (am[i] & (1u << lane)) {
+            const bool act = (am[i] >> lane) & 1;
+            if (a.SA) a.SA[slot[i]] = p[i];
+            if (a.isa_all || act) a.ISA[p[i]] = rank;
+            if (a.rows) {
+                if (ROUND0) a.rows[slot[i]] = (u8)(pc[i >> 2] >> (8 * (i & 3)));
+                else if (!act && p[i] != 0) a.rows[slot[i]] = a.text[p[i] - 1];
+            }
+            if (act) {
                 u32 o = c_act + __popc(am[i] & lt);
-                a_pos[o] = p[i];
-                a_slot[o] = slot[i];
-                a_grp[o] = c_grp + __popc(gm[i] & le) - 1;
+                a.a_pos[o] = p[i];
+                a.a_slot[o] = slot[i];
+                a.a_grp[o] = c_grp + __popc(gm[i] & le) - 1;
+            } else {
+                // final: this suffix's slot will never change again
+                if (p[i] == 0) *a.primary = (u64)slot[i] + 1;
+                if (a.aux_I && ((u64)p[i] & a.aux_mask) == 0) a.aux_I[p[i] >> a.aux_shift] = slot[i] + 1;
             }
         }
         if (hm[i]) c_head = __shfl_sync(0xffffffffu, slot[i], 31 - __clz(hm[i]));
@@ -251,17 +296,55 @@ rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, const u32
     }
 }
 
+// After round 0, when many suffixes stay active the full ISA is needed: ranks of the singletons.
+__global__ void __launch_bounds__(256)
+isa_fill_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N, u64 tail_start, int key_shift,
+                u32 *__restrict__ ISA)
+{
+    u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    u64 k = keys[j] >> key_shift;
+    u32 p = pos[j];
+    bool tail = (u64)p >= tail_start;
+    bool head = (j == 0) || ((keys[j - 1] >> key_shift) != k) || tail || (u64)pos[j - (j ? 1 : 0)] >= tail_start;
+    bool nexthead = (j + 1 == N) || ((keys[j + 1] >> key_shift) != k) || tail || (u64)pos[j + (j + 1 < N ? 1 : 0)] >= tail_start;
+    if (head && nexthead) ISA[p] = (u32)j;
+}
+
+// Lazy ISA: rank of a round-0 singleton q, recomputed from the sorted round-0 keys.
+struct LazyArgs { const u64 *words; int b; int K; const u64 *s0_keys; const u32 *s0_pos; int key_shift; u64 tail_start; u64 n; };
+
+__device__ __forceinline__ u32 lazy_rank(const LazyArgs &la, u64 q)
+{
+    const u64 kq = kmer_at(la.words, q, la.b, la.K);
+    u64 lo = 0, hi = la.n;                               // lower bound of kq among the sorted k-mers
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if ((la.s0_keys[mid] >> la.key_shift) < kq) lo = mid + 1; else hi = mid;
+    }
+    u64 s = lo;
+    if (q >= la.tail_start) { while (s + 1 < la.n && (u64)la.s0_pos[s] != q) ++s; }       // its own slot
+    else { while (s + 1 < la.n && (u64)la.s0_pos[s] >= la.tail_start) ++s; }              // first full-length suffix
+    return (u32)s;
+}
+
 // round >= 1 keys: (dense group id, rank of the suffix h positions further + 1)
+template <bool LAZY>
 __global__ void __launch_bounds__(256)
 round_keys_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp,
                   const u32 *__restrict__ ISA, u64 N, u64 n, u64 h, int rank_bits,
-                  u64 *__restrict__ keys, u32 *__restrict__ pos)
+                  u64 *__restrict__ keys, u32 *__restrict__ pos, const LazyArgs la)
 {
     u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
     if (j >= N) return;
     u32 p = a_pos[j];
     u64 q = (u64)p + h;
-    u64 k2 = q < n ? (u64)ISA[q] + 1 : 0;
+    u64 k2 = 0;
+    if (q < n) {
+        u32 r = ISA[q];
+        if (LAZY && r == kIsaInvalid) r = lazy_rank(la, q);
+        k2 = (u64)r + 1;
+    }
     keys[j] = ((u64)a_grp[j] << rank_bits) | k2;
     pos[j] = p;
 }
@@ -276,14 +359,15 @@ size_t sa_workspace_bytes(u64 n, int sym_bytes)
     else if (sym_bytes == 4) nw = ceil_div(n * 32, 64) + 4;
     size_t per = (size_t)n * (8 + 8 + 4 + 4      /* keys, vals (ping-pong) */
                               + 4 + 4            /* SA, ISA */
-                              + 4 + 4 + 4 + 4);  /* a_pos, a_grp, a_slot x2 */
+                              + 4 + 4 + 4 + 4    /* a_pos, a_grp, a_slot x2 */
+                              + 1);              /* lazy mode: separate small round buffers */
     size_t st = 3 * ceil_div(n, kRankTile) * sizeof(u64);
-    return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + 256 + 16 * 256 + 4096;
+    return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + 256 + 32 * 256 + 4096;
 }
 
-static int choose_key_symbols(u64 n, int b, double entropy_bits)
+static int choose_key_symbols(u64 n, int b, double entropy_bits, int max_key_bits)
 {
-    int kmax = 64 / b;
+    int kmax = max_key_bits / b;
     if (kmax < 1) kmax = 1;
     const char *env = getenv("LIBSAIS_CUDA_KEY_SYMBOLS");
     if (env && *env) { int k = atoi(env); if (k >= 1) return k < kmax ? k : kmax; }
@@ -300,11 +384,21 @@ static int choose_key_symbols(u64 n, int b, double entropy_bits)
     return k2 > k ? k2 : k;
 }
 
-int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResult *out)
+static bool read_round_scalars(Ctx &c)
+{
+    c.check(cudaMemcpyAsync(c.h_scalars + S_ERR, c.d_scalars + S_ERR, (S_PRIMARY - S_ERR + 1) * sizeof(u64),
+                            cudaMemcpyDeviceToHost, c.stream));
+    if (!c.sync()) return false;
+    if (c.h_scalars[S_ERR] != 0) { c.last_error = cudaErrorLaunchTimeout; return false; }
+    return true;
+}
+
+int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt, SAResult *out)
 {
     if (n == 0) return 0;
     if (n > kMaxN) return -2;
     cudaStream_t st = c.stream;
+    const bool bwt_mode = opt.bwt_rows != nullptr && sym_bytes == 1;
 
     // ---- alphabet: bits per symbol, order-preserving code map (bytes), key width
     int b = 8; double entropy = 8.0;
@@ -337,7 +431,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResul
         b = bits_for(c.h_scalars[S_MAXSYM]);
         entropy = (double)b;            // unknown distribution: assume dense
     }
-    const int k = choose_key_symbols(n, b, entropy);
+    const int key_shift = bwt_mode ? 8 : 0;
+    const int k = choose_key_symbols(n, b, entropy, 64 - key_shift);
     const int K = k * b;
 
     // ---- arena
@@ -345,16 +440,18 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResul
     u64 *words = c.alloc_n<u64>(nwords);
     u64 *keyA = c.alloc_n<u64>(n), *keyB = c.alloc_n<u64>(n);
     u32 *valA = c.alloc_n<u32>(n), *valB = c.alloc_n<u32>(n);
-    u32 *SA = sa_out ? sa_out : c.alloc_n<u32>(n), *ISA = c.alloc_n<u32>(n);
+    u32 *SA = opt.want_sa ? (opt.sa_out ? opt.sa_out : c.alloc_n<u32>(n)) : nullptr;
+    u32 *ISA = c.alloc_n<u32>(n);
     u32 *a_pos = c.alloc_n<u32>(n), *a_grp = c.alloc_n<u32>(n);
     u32 *a_slot0 = c.alloc_n<u32>(n), *a_slot1 = c.alloc_n<u32>(n);
     const u64 rank_tiles = ceil_div(n, kRankTile);
     u64 *rstatus = c.alloc_n<u64>(3 * rank_tiles);
     void *sort_temp = c.alloc(RadixSort<u64, u32>::temp_bytes(n));
-    if (!sort_temp || !rstatus || !a_slot1) return -2;
+    if (!sort_temp || !rstatus || !a_slot1 || (opt.want_sa && !SA)) return -2;
     u32 *err = (u32 *)(c.d_scalars + S_ERR);
     u32 *tickets = (u32 *)(c.d_scalars + S_TICKET);
     c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, (S_MISC - S_ERR) * sizeof(u64), st));
+    c.check(cudaMemsetAsync(ISA, 0xFF, n * sizeof(u32), st));                  // kIsaInvalid everywhere
 
     // ---- pack + initial keys
     {
@@ -363,30 +460,52 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResul
         if (sym_bytes == 1) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u8, true>), grid, 256, 0, (const u8 *)d_T, n, b, words, nwords, d_lut);
         else if (sym_bytes == 4) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u32, false>), grid, 256, 0, (const u32 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
         else LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u64, false>), grid, 256, 0, (const u64 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
-        LSC_LAUNCH(c, KC_MAKE_KEYS, (double)nwords * 8 + (double)n * 12, make_keys_kernel,
-                   (u32)ceil_div(n, 256), 256, 0, words, n, b, K, keyA, valA);
+        LSC_LAUNCH(c, KC_MAKE_KEYS, (double)nwords * 8 + (double)n * (12 + (bwt_mode ? 1 : 0)), make_keys_kernel,
+                   (u32)ceil_div(n, 256), 256, 0, words, n, b, K, key_shift, bwt_mode ? (const u8 *)d_T : (const u8 *)nullptr, keyA, valA);
     }
 
     // ---- round 0: sort by the k-mer, rank, compact
     RoundStat rs; rs.h = 0; rs.n_active = n; rs.key_bits = K; rs.passes = 0; rs.n_groups = 0;
-    int where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, n, 0, K, sort_temp, err, &rs.passes);
+    int where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, n, key_shift, key_shift + K, sort_temp, err, &rs.passes);
     if (where < 0) return -2;
-    u64 *ks = where ? keyB : keyA; u32 *vs = where ? valB : valA;
+    u64 *ks = where ? keyB : keyA; u32 *vs = where ? valB : valA;      // S0: sorted round-0 (key, pos)
     u64 *ko = where ? keyA : keyB; u32 *vo = where ? valA : valB;
     u32 *slot_cur = a_slot0, *slot_nxt = a_slot1;
-    {
-        c.check(cudaMemsetAsync(rstatus, 0, 3 * rank_tiles * sizeof(u64), st));
-        const u64 tail_start = n >= (u64)k ? n - (u64)k + 1 : 0;
-        LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + 8), rank_kernel<true>, (u32)rank_tiles, kRankThreads, 0,
-                   ks, vs, (const u32 *)nullptr, n, tail_start, SA, ISA, a_pos, slot_cur, a_grp,
-                   rstatus, rank_tiles, tickets + 0, c.d_scalars + S_NACT, err);
-    }
-    c.check(cudaMemcpyAsync(c.h_scalars + S_ERR, c.d_scalars + S_ERR, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    if (!c.sync()) return -2;
-    if (c.h_scalars[S_ERR] != 0) { c.last_error = cudaErrorLaunchTimeout; return -2; }
+    const u64 tail_start = n >= (u64)k ? n - (u64)k + 1 : 0;
+
+    RankArgs ra;
+    ra.keys = ks; ra.pos = vs; ra.slot_in = nullptr; ra.N = n; ra.tail_start = tail_start; ra.key_shift = key_shift;
+    ra.SA = SA; ra.ISA = ISA; ra.isa_all = 0;
+    ra.rows = bwt_mode ? opt.bwt_rows : nullptr; ra.text = bwt_mode ? (const u8 *)d_T : nullptr;
+    ra.aux_I = opt.aux_I; ra.aux_mask = opt.aux_I ? opt.aux_r - 1 : 0; ra.aux_shift = opt.aux_I ? bits_for(opt.aux_r) - 1 : 0;
+    ra.primary = c.d_scalars + S_PRIMARY;
+    ra.a_pos = a_pos; ra.a_slot = slot_cur; ra.a_grp = a_grp;
+    ra.status = rstatus; ra.ntiles = rank_tiles; ra.ticket = tickets + 0; ra.out_counts = c.d_scalars + S_NACT; ra.err = err;
+    c.check(cudaMemsetAsync(rstatus, 0, 3 * rank_tiles * sizeof(u64), st));
+    LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+    if (!read_round_scalars(c)) return -2;
     u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
     rs.n_groups = G;
     c.rounds.push_back(rs);
+
+    // ---- lazy ISA: with few active suffixes the ranks of round-0 singletons are never scattered;
+    // the rare look-ups that hit one recompute it by binary search in the sorted round-0 keys.
+    bool lazy = N * 32 <= n;
+    { const char *env = getenv("LIBSAIS_CUDA_LAZY_ISA"); if (env && *env) lazy = atoi(env) != 0; }
+    u64 *rk0 = ks, *rk1 = ko; u32 *rv0 = vs, *rv1 = vo;
+    if (N > 0) {
+        if (lazy) {
+            rk0 = c.alloc_n<u64>(N); rk1 = c.alloc_n<u64>(N); rv0 = c.alloc_n<u32>(N); rv1 = c.alloc_n<u32>(N);
+            if (!rv1 || !rk1 || !rk0 || !rv0) {                 // no room for separate buffers: fall back to the full ISA
+                lazy = false; rk0 = ks; rk1 = ko; rv0 = vs; rv1 = vo; c.last_error = cudaSuccess;
+            }
+        }
+        if (!lazy)
+            LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + 4), isa_fill_kernel, (u32)ceil_div(n, 256), 256, 0,
+                       ks, vs, n, tail_start, key_shift, ISA);
+    }
+    LazyArgs la; la.words = words; la.b = b; la.K = K; la.s0_keys = ks; la.s0_pos = vs; la.key_shift = key_shift;
+    la.tail_start = tail_start; la.n = n;
 
     // ---- doubling rounds on the active suffixes
     const int rank_bits = bits_for(n);                 // k2 = ISA+1 <= n
@@ -396,21 +515,19 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResul
         if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
         const int grp_bits = bits_for(G > 1 ? G - 1 : 1);
         RoundStat r; r.h = h; r.n_active = N; r.key_bits = rank_bits + grp_bits; r.passes = 0; r.n_groups = 0;
-        // keys go to the pair not holding anything live (everything in ks/vs is dead by now)
-        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel, (u32)ceil_div(N, 256), 256, 0,
-                   a_pos, a_grp, ISA, N, n, h, rank_bits, ks, vs);
-        where = RadixSort<u64, u32>::sort(c, ks, vs, ko, vo, N, 0, rank_bits + grp_bits, sort_temp, err, &r.passes);
+        if (lazy) LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel<true>, (u32)ceil_div(N, 256), 256, 0,
+                             a_pos, a_grp, ISA, N, n, h, rank_bits, rk0, rv0, la);
+        else      LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel<false>, (u32)ceil_div(N, 256), 256, 0,
+                             a_pos, a_grp, ISA, N, n, h, rank_bits, rk0, rv0, la);
+        where = RadixSort<u64, u32>::sort(c, rk0, rv0, rk1, rv1, N, 0, rank_bits + grp_bits, sort_temp, err, &r.passes);
         if (where < 0) return -2;
-        const u64 *sk = where ? ko : ks; const u32 *sv = where ? vo : vs;
         const u64 tiles = ceil_div(N, kRankTile);
         c.check(cudaMemsetAsync(rstatus, 0, 3 * rank_tiles * sizeof(u64), st));
         c.check(cudaMemsetAsync(tickets + (round & 7), 0, sizeof(u32), st));
-        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 8), rank_kernel<false>, (u32)tiles, kRankThreads, 0,
-                   sk, sv, slot_cur, N, (u64)0, SA, ISA, a_pos, slot_nxt, a_grp,
-                   rstatus, tiles, tickets + (round & 7), c.d_scalars + S_NACT, err);
-        c.check(cudaMemcpyAsync(c.h_scalars + S_ERR, c.d_scalars + S_ERR, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-        if (!c.sync()) return -2;
-        if (c.h_scalars[S_ERR] != 0) { c.last_error = cudaErrorLaunchTimeout; return -2; }
+        ra.keys = where ? rk1 : rk0; ra.pos = where ? rv1 : rv0; ra.slot_in = slot_cur; ra.N = N; ra.tail_start = 0; ra.key_shift = 0;
+        ra.isa_all = 1; ra.a_slot = slot_nxt; ra.ntiles = tiles; ra.ticket = tickets + (round & 7);
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 8), rank_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        if (!read_round_scalars(c)) return -2;
         N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
         r.n_groups = G;
         c.rounds.push_back(r);
@@ -418,7 +535,9 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, u32 *sa_out, SAResul
         h *= 2;
         ++round;
     }
-    out->SA = SA; out->ISA = ISA; out->scratch = keyA; out->scratch_bytes = (size_t)n * 8;
+    out->SA = SA; out->ISA = ISA; out->isa_complete = !lazy;
+    out->primary = c.h_scalars[S_PRIMARY];
+    out->scratch = keyA; out->scratch_bytes = (size_t)n * 8;
     return c.failed() ? -2 : 0;
 }
 

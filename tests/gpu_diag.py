@@ -76,6 +76,15 @@ def main():
             nbad += 1
             print("int:%s rc=%d %s" % (name, a[0], d), flush=True)
     print("cases failed:", nbad, "of", len(allc) + len(cases.int_cases()))
+    import os
+    for lazy in ("0", "1"):
+        os.environ["LIBSAIS_CUDA_LAZY_ISA"] = lazy
+        nb = 0
+        for name, T in allc:
+            if len(T) > 1 and not run_case(name + "/lazy" + lazy, T, cu, o):
+                nb += 1
+        print("forced lazy=%s: cases failed: %d" % (lazy, nb), flush=True)
+    del os.environ["LIBSAIS_CUDA_LAZY_ISA"]
     # stats of one call
     ctx = libsais_b200.Context(0)
     T = gen.rand_bytes(2, 1 << 24)
