@@ -27,6 +27,7 @@ enum KernelClass {
     KC_SORT_SCAN,      // digit-base exclusive scan
     KC_SORT_PASS,      // onesweep digit pass (the dominant kernel)
     KC_RANK_INIT,      // round-0 head flags + rank + ISA scatter + compaction
+    KC_RANK_SCAN,      // scan of the rank stage's tile aggregates
     KC_ROUND_KEYS,     // round>=1 key build (ISA gather)
     KC_RANK_UPDATE,    // round>=1 rank update + ISA scatter + compaction
     KC_SMALL_SORT,     // round>=1 in-shared-memory sort of small active sets
@@ -42,7 +43,7 @@ enum KernelClass {
 };
 
 static const char *const kKernelClassName[KC_COUNT] = {
-    "hist_sym", "pack", "make_keys", "sort_hist", "sort_scan", "sort_pass", "rank_init",
+    "hist_sym", "pack", "make_keys", "sort_hist", "sort_scan", "sort_pass", "rank_init", "rank_scan",
     "round_keys", "rank_update", "small_sort", "bwt", "phi", "plcp", "lcp",
     "unbwt_prep", "unbwt_walk", "unbwt_rank", "convert"
 };

@@ -49,12 +49,22 @@ static inline SortPlan make_sort_plan(int lo_bit, int hi_bit)
 template <typename KeyT>
 __device__ __forceinline__ u32 digit_of(KeyT k, int shift, u32 mask) { return (u32)(k >> shift) & mask; }
 
+// Key/value source of the FIRST pass.  NoGen: read the (key, value) arrays.  A generator type
+// (kActive = true; key(i), val(i) device functions) produces element i on the fly instead, so
+// the initial key array is never materialised: the histogram kernel and the first digit pass
+// both evaluate the generator (sa_core.cu: k-mer keys straight from the packed text).
+struct NoGen {
+    static const bool kActive = false;
+    __device__ __forceinline__ u64 key(u64) const { return 0; }
+    __device__ __forceinline__ u32 val(u64) const { return 0; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Upfront histograms of all digits: hist[pass][256] (u64).  One read of the keys.
 // ---------------------------------------------------------------------------------------------
-template <typename KeyT, int THREADS>
+template <typename KeyT, int THREADS, typename Gen>
 __global__ void __launch_bounds__(THREADS)
-sort_hist_kernel(const KeyT *__restrict__ keys, u64 n, SortPlan plan, u64 *__restrict__ hist)
+sort_hist_kernel(const KeyT *__restrict__ keys, u64 n, SortPlan plan, u64 *__restrict__ hist, const Gen gen)
 {
     __shared__ u32 sh[kMaxPasses * kRadixSize];
     const int P = plan.passes;
@@ -65,7 +75,7 @@ sort_hist_kernel(const KeyT *__restrict__ keys, u64 n, SortPlan plan, u64 *__res
     for (u64 r = 0; r < rounds; ++r) {
         u64 idx = r * stride + (u64)blockIdx.x * THREADS + threadIdx.x;
         bool valid = idx < n;
-        KeyT k = valid ? keys[idx] : (KeyT)0;
+        KeyT k = valid ? (Gen::kActive ? (KeyT)gen.key(idx) : keys[idx]) : (KeyT)0;
         for (int p = 0; p < P; ++p) {
             u32 d = digit_of(k, plan.shift[p], (1u << plan.nbits[p]) - 1);
             u32 d0 = __shfl_sync(0xffffffffu, d, 0);
@@ -102,11 +112,16 @@ static __global__ void sort_scan_kernel(const u64 *__restrict__ hist, u64 *__res
 }
 
 // ---------------------------------------------------------------------------------------------
-// One digit pass.
-//   VALS : 0 = values loaded late (scatter phase), 1 = loaded early into registers,
-//          2 = prefetched into shared memory with cp.async (no registers, latency overlapped)
-//   EARLY: publish the tile's digit counts before the ranking (counting pre-pass with
-//          shared-memory atomics) so successors' look-back rarely finds an unpublished tile
+// One digit pass.  Template knobs:
+//   VALS   : 1 = values loaded with the keys into registers, 2 = prefetched into shared memory
+//            with cp.async (no registers; latency overlapped with the ranking)
+//   NMATCH : how many of a thread's IPT items are ranked with match.any (one instruction, but
+//            the shared ADU pipe runs it at ~2 cycles per lane); the rest use 8 ballots (ALU).
+//            Splitting the items balances the two pipes.
+// Phases of a tile: load -> digit counts (shared atomics) -> publish counts EARLY, before the
+// long ranking phase, so successors' look-back rarely meets an unpublished tile -> warp-level
+// multisplit ranking -> per-digit scan over warps + decoupled look-back -> scatter into shared
+// memory in sorted order -> coalesced write-out of each digit's run.
 // ---------------------------------------------------------------------------------------------
 template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS>
 struct PassSmem {
@@ -115,9 +130,8 @@ struct PassSmem {
     u64  goff[kRadixSize];                 // global offset of a digit's run minus its offset in the tile
     ValT vals[TILE];
     ValT vals_in[VALS == 2 ? TILE : 1];
-    u32  whist[(THREADS / 32) * kRadixSize];
-    u32  tileoff[kRadixSize];
-    u32  early[kRadixSize];
+    alignas(16) u32 whist[(THREADS / 32) * kRadixSize];   // zeroed with 16-byte stores
+    u32  cnt[kRadixSize];
     u32  scan_tmp[32];
     u32  tile;
 };
@@ -168,66 +182,76 @@ __device__ __forceinline__ u64 lookback_digit(u64 *status, u32 tile, u32 digit, 
     return excl;
 }
 
-template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, bool EARLY>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 2))
-sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
-                 KeyT *__restrict__ kout, ValT *__restrict__ vout, u64 n,
-                 int shift, u32 dmask, const u64 *__restrict__ base,
-                 u64 *status, u32 *ticket, u32 *err)
+// peers of this lane: lanes whose (valid) item has the same digit
+template <bool USE_MATCH>
+__device__ __forceinline__ u32 digit_peers(u32 d, bool valid, int lane)
 {
-    typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
+    if (USE_MATCH) return __match_any_sync(0xffffffffu, d);        // invalid items carry d = 256: their own class
+    u32 peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int bit = 0; bit < kRadixBits; ++bit) {
+        bool on = (d >> bit) & 1;
+        u32 m = __ballot_sync(0xffffffffu, on);
+        peers &= on ? m : ~m;
+    }
+    return valid ? peers : (1u << lane);
+}
+
+template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, int NMATCH, bool FULL, typename Gen>
+__device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT, VALS> &sm, const Gen &gen,
+                                               const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
+                                               KeyT *__restrict__ kout, ValT *__restrict__ vout,
+                                               const u32 tile, const u32 count, int shift, u32 dmask,
+                                               const u64 *__restrict__ base, u64 *status, u32 *err)
+{
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * IPT;
-    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one thread per digit is assumed");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < WARPS * kRadixSize; i += THREADS) sm.whist[i] = 0;
-    if (EARLY && tid < kRadixSize) sm.early[tid] = 0;
-    __syncthreads();
-    const u32 tile = sm.tile;
     const u64 tile_base = (u64)tile * TILE;
-    const u32 count = (u32)((n - tile_base) < (u64)TILE ? (n - tile_base) : (u64)TILE);
+    kin += tile_base; vin += tile_base;
 
-    // ---- load keys, warp-striped (element order inside the tile = (warp, item, lane))
+    // ---- load keys (+ values), warp-striped: element order inside the tile = (warp, item, lane)
     KeyT key[IPT];
     ValT val[VALS == 1 ? IPT : 1];
     const u32 wbase = warp * (IPT * 32) + lane;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 li = wbase + i * 32;
-        key[i] = li < count ? kin[tile_base + li] : (KeyT)0;
+        key[i] = (FULL || li < count) ? (Gen::kActive ? (KeyT)gen.key(tile_base + li) : kin[li]) : (KeyT)0;
     }
-    if (VALS == 1) {
+    if (Gen::kActive) {
+        // values are recomputed at scatter time
+    } else if (VALS == 1) {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             u32 li = wbase + i * 32;
-            val[VALS == 1 ? i : 0] = li < count ? vin[tile_base + li] : (ValT)0;
+            val[VALS == 1 ? i : 0] = (FULL || li < count) ? vin[li] : (ValT)0;
         }
-    } else if (VALS == 2) {
+    } else {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             u32 li = wbase + i * 32;
-            if (li < count) cp_async4(&sm.vals_in[VALS == 2 ? li : 0], vin + tile_base + li);
+            if (FULL || li < count) cp_async4(&sm.vals_in[VALS == 2 ? li : 0], vin + li);
         }
     }
 
-    u32 cnt = 0;
-    if (EARLY) {
-        // counting pre-pass: tile digit counts, published before the (longer) ranking phase
+    // ---- counting pre-pass: the tile's digit counts, published before the (longer) ranking phase
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            u32 li = wbase + i * 32;
-            if (li < count) atomicAdd(&sm.early[digit_of(key[i], shift, dmask)], 1u);
-        }
-        __syncthreads();
-        if (tid < kRadixSize) {
-            cnt = sm.early[tid];
-            st_relaxed(status + (u64)tile * kRadixSize + tid, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
-        }
+    for (int i = 0; i < IPT; ++i) {
+        u32 li = wbase + i * 32;
+        if (FULL || li < count) atomicAdd(&sm.cnt[digit_of(key[i], shift, dmask)], 1u);
+    }
+    __syncthreads();
+    u32 cnt = 0, tileoff = 0;
+    if (tid < kRadixSize) {
+        cnt = sm.cnt[tid];
+        st_relaxed(status + (u64)tile * kRadixSize + tid, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
+        // exclusive scan of the 256 counts: warp scan + totals of the 8 digit warps
+        u32 x = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+        if (lane == 31) sm.scan_tmp[warp] = x;
+        tileoff = x - cnt;
     }
 
     // ---- warp-level multisplit: rank of every item among the items of its warp with the same digit
@@ -237,9 +261,9 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 li = wbase + i * 32;
-        bool valid = li < count;
+        bool valid = FULL || li < count;
         u32 d = valid ? digit_of(key[i], shift, dmask) : (u32)kRadixSize;
-        u32 peers = __match_any_sync(0xffffffffu, d);
+        u32 peers = (i < NMATCH) ? digit_peers<true>(d, valid, lane) : digit_peers<false>(d, valid, lane);
         int leader = __ffs(peers) - 1;
         u32 old = 0;
         if (lane == leader && valid) { old = wh[d]; wh[d] = old + __popc(peers); }
@@ -249,59 +273,28 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     }
     __syncthreads();
 
-    // ---- per digit: exclusive scan over the warps, tile count
+    // ---- per digit: offsets of every warp's run inside the tile, then the chained scan over tiles
     if (tid < kRadixSize) {
-        u32 sum = 0;
+#pragma unroll
+        for (int w = 0; w < kRadixSize / 32; ++w) if (w < warp) tileoff += sm.scan_tmp[w];
+        u32 sum = tileoff;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) { u32 t = sm.whist[w * kRadixSize + tid]; sm.whist[w * kRadixSize + tid] = sum; sum += t; }
-        if (!EARLY) {
-            cnt = sum;
-            st_relaxed(status + (u64)tile * kRadixSize + tid, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
-        }
-    }
-    // exclusive scan of the 256 tile counts (threads >= 256 carry 0)
-    {
-        u32 x = cnt;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
-        if (lane == 31) sm.scan_tmp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            u32 v = lane < WARPS ? sm.scan_tmp[lane] : 0;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += y; }
-            sm.scan_tmp[lane] = v;                     // inclusive over warps
-        }
-        __syncthreads();
-        u32 warp_excl = warp ? sm.scan_tmp[warp - 1] : 0;
-        if (tid < kRadixSize) sm.tileoff[tid] = warp_excl + x - cnt;
-    }
-    // ---- chained scan over tiles
-    if (tid < kRadixSize) {
         u64 excl = lookback_digit(status, tile, (u32)tid, cnt, err);
-        sm.goff[tid] = base[tid] + excl - (u64)sm.tileoff[tid];
+        sm.goff[tid] = base[tid] + excl - (u64)tileoff;
     }
-    if (VALS == 2) cp_async_wait_all();
+    if (VALS == 2 && !Gen::kActive) cp_async_wait_all();
     __syncthreads();
 
     // ---- scatter keys and values into their place inside the tile (shared memory)
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 li = wbase + i * 32;
-        if (li < count) {
-            u32 d = digit_of(key[i], shift, dmask);
-            u32 pos = sm.tileoff[d] + wh[d] + rnk[i];
+        if (FULL || li < count) {
+            u32 pos = wh[digit_of(key[i], shift, dmask)] + rnk[i];
             sm.keys[pos] = key[i];
-            if (VALS == 1) sm.vals[pos] = val[VALS == 1 ? i : 0];
-            else if (VALS == 2) sm.vals[pos] = sm.vals_in[VALS == 2 ? li : 0];
-            else rnk[i] = pos;
-        }
-    }
-    if (VALS == 0) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            u32 li = wbase + i * 32;
-            if (li < count) sm.vals[rnk[i]] = vin[tile_base + li];
+            sm.vals[pos] = Gen::kActive ? (ValT)gen.val(tile_base + li)
+                                        : (VALS == 1 ? val[VALS == 1 ? i : 0] : sm.vals_in[VALS == 2 ? li : 0]);
         }
     }
     __syncthreads();
@@ -310,7 +303,7 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 idx = i * THREADS + tid;
-        if (idx < count) {
+        if (FULL || idx < count) {
             KeyT k = sm.keys[idx];
             u64 g = sm.goff[digit_of(k, shift, dmask)] + idx;
             kout[g] = k;
@@ -319,17 +312,44 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Host driver
-// ---------------------------------------------------------------------------------------------
-// Tuning variants of the pass kernel, selectable with LIBSAIS_CUDA_SORT_VARIANT for experiments.
-struct PassVariant { int threads, ipt, vals, early; };
-static const PassVariant kPassVariants[] = {
-    {256, 16, 0, 0}, {256, 16, 2, 0}, {256, 16, 2, 1}, {512, 8, 1, 0}, {512, 8, 1, 1}, {512, 8, 2, 1},
-    {384, 12, 2, 1}, {256, 16, 0, 1},
-};
+template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, int NMATCH, typename Gen>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : (THREADS <= 512 ? 2 : 1)))
+sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
+                 KeyT *__restrict__ kout, ValT *__restrict__ vout, u64 n,
+                 int shift, u32 dmask, const u64 *__restrict__ base,
+                 u64 *status, u32 *ticket, u32 *err, const Gen gen)
+{
+    typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * IPT;
+    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one thread per digit is assumed");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(sm.whist);
+        for (int i = tid; i < WARPS * kRadixSize / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        if (tid < kRadixSize) sm.cnt[tid] = 0;
+    }
+    __syncthreads();
+    const u32 tile = sm.tile;
+    const u64 tile_base = (u64)tile * TILE;
+    const u32 count = (u32)((n - tile_base) < (u64)TILE ? (n - tile_base) : (u64)TILE);
+    if (count == TILE)
+        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, NMATCH, true, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
+    else
+        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, NMATCH, false, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
+}
+
+// Tile shapes of the pass kernel; LIBSAIS_CUDA_SORT_VARIANT selects one for experiments.
+// Measured on B200, 2^28 (u64,u32) pairs, 8-bit digits (profiles/sort_pass_variants_r1.md):
+// two to three independent CTAs per SM beat one large CTA; 384 x 12 is the fastest.
+struct PassVariant { int threads, ipt, vals; };
+static const PassVariant kPassVariants[] = { {384, 12, 2}, {512, 8, 1}, {256, 16, 2} };
 static const int kNumPassVariants = sizeof(kPassVariants) / sizeof(kPassVariants[0]);
-static const int kDefaultPassVariant = 2;
+static const int kDefaultPassVariant = 0;
 
 static inline int pass_variant()
 {
@@ -356,26 +376,40 @@ struct RadixSort {
              + ceil_div(n, 3072) * kRadixSize * sizeof(u64);  // status of one pass (smallest tile of any variant)
     }
 
-    template <int THREADS, int IPT, int VALS, bool EARLY>
-    static void launch_pass(Ctx &c, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout, u64 n, int shift, u32 dmask,
-                            const u64 *base, u64 *status, u32 *ticket, u32 *err)
+    template <int THREADS, int IPT, int VALS, typename Gen>
+    static void launch_pass(Ctx &c, const Gen &gen, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout, u64 n,
+                            int shift, u32 dmask, const u64 *base, u64 *status, u32 *ticket, u32 *err)
     {
         typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
-        auto kern = sort_pass_kernel<KeyT, ValT, THREADS, IPT, VALS, EARLY>;
+        auto kern = sort_pass_kernel<KeyT, ValT, THREADS, IPT, VALS, 0, Gen>;
         c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         u64 nt = ceil_div(n, (u64)THREADS * IPT);
-        LSC_LAUNCH(c, KC_SORT_PASS, 2.0 * (double)n * (sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
-                   kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err);
+        const double in_bytes = Gen::kActive ? 2.0 : (double)(sizeof(KeyT) + sizeof(ValT));   // generator: packed text + bwt byte
+        LSC_LAUNCH(c, KC_SORT_PASS, (double)n * (in_bytes + sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
+                   kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err, gen);
     }
 
-    // Sort n pairs on key bits [lo_bit, hi_bit).  Input in (ka, va); (kb, vb) is the alternate
+    template <typename Gen>
+    static void pass(Ctx &c, const Gen &gen, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout, u64 n,
+                     int shift, u32 dmask, const u64 *base, u64 *status, u32 *ticket, u32 *err)
+    {
+        switch (pass_variant()) {
+        case 1:  launch_pass<512, 8, 1, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err); break;
+        case 2:  launch_pass<256, 16, 2, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err); break;
+        default: launch_pass<384, 12, 2, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err); break;
+        }
+    }
+
+    // Sort n pairs on key bits [lo_bit, hi_bit).  Input in (ka, va) -- or produced by `gen` when
+    // Gen::kActive, in which case (ka, va) is only the alternate buffer; (kb, vb) is the other
     // buffer.  Returns 0 when the result is in (ka, va), 1 when in (kb, vb), -1 on error.
-    static int sort(Ctx &c, KeyT *ka, ValT *va, KeyT *kb, ValT *vb, u64 n, int lo_bit, int hi_bit,
-                    void *temp, u32 *err, int *passes_out = nullptr)
+    template <typename Gen>
+    static int sort_from(Ctx &c, const Gen &gen, KeyT *ka, ValT *va, KeyT *kb, ValT *vb, u64 n, int lo_bit, int hi_bit,
+                         void *temp, u32 *err, int *passes_out = nullptr)
     {
         SortPlan plan = make_sort_plan(lo_bit, hi_bit);
         if (passes_out) *passes_out = plan.passes;
-        if (n == 0 || plan.passes == 0) return 0;
+        if (n == 0 || plan.passes == 0) return Gen::kActive ? -1 : 0;
         char *t = (char *)temp;
         u64 *hist = (u64 *)t;               t += kMaxPasses * kRadixSize * sizeof(u64);
         u64 *base = (u64 *)t;               t += kMaxPasses * kRadixSize * sizeof(u64);
@@ -387,33 +421,29 @@ struct RadixSort {
         {
             u64 want = ceil_div(n, (u64)HIST_THREADS * 8);
             u32 grid = (u32)(want < (u64)c.sm_count * 4 ? (want ? want : 1) : (u64)c.sm_count * 4);
-            LSC_LAUNCH(c, KC_SORT_HIST, (double)n * sizeof(KeyT), (sort_hist_kernel<KeyT, HIST_THREADS>),
-                       grid, HIST_THREADS, 0, ka, n, plan, hist);
+            LSC_LAUNCH(c, KC_SORT_HIST, (double)n * (Gen::kActive ? 2.0 : (double)sizeof(KeyT)), (sort_hist_kernel<KeyT, HIST_THREADS, Gen>),
+                       grid, HIST_THREADS, 0, ka, n, plan, hist, gen);
         }
         LSC_LAUNCH(c, KC_SORT_SCAN, 0.0, sort_scan_kernel, plan.passes, kRadixSize, 0, hist, base);
 
         KeyT *kin = ka, *kout = kb; ValT *vin = va, *vout = vb;
         int where = 0;
-        const int variant = pass_variant();
         for (int p = 0; p < plan.passes; ++p) {
             c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * sizeof(u64), c.stream));
             const int shift = plan.shift[p]; const u32 dmask = (1u << plan.nbits[p]) - 1;
-            const u64 *bp = base + p * kRadixSize; u32 *tk = tickets + p;
-            switch (variant) {
-            case 0: launch_pass<256, 16, 0, false>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            case 1: launch_pass<256, 16, 2, false>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            case 2: launch_pass<256, 16, 2, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            case 3: launch_pass<512, 8, 1, false>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            case 4: launch_pass<512, 8, 1, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            case 5: launch_pass<512, 8, 2, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            case 6: launch_pass<384, 12, 2, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            default: launch_pass<256, 16, 0, true>(c, kin, vin, kout, vout, n, shift, dmask, bp, status, tk, err); break;
-            }
+            if (p == 0 && Gen::kActive) pass<Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, tickets, err);
+            else pass<NoGen>(c, NoGen(), kin, vin, kout, vout, n, shift, dmask, base + p * kRadixSize, status, tickets + p, err);
             KeyT *tk2 = kin; kin = kout; kout = tk2;
             ValT *tv = vin; vin = vout; vout = tv;
             where ^= 1;
         }
         return c.failed() ? -1 : where;
+    }
+
+    static int sort(Ctx &c, KeyT *ka, ValT *va, KeyT *kb, ValT *vb, u64 n, int lo_bit, int hi_bit,
+                    void *temp, u32 *err, int *passes_out = nullptr)
+    {
+        return sort_from<NoGen>(c, NoGen(), ka, va, kb, vb, n, lo_bit, hi_bit, temp, err, passes_out);
     }
 };
 

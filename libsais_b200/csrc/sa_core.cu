@@ -113,7 +113,25 @@ __device__ __forceinline__ u64 kmer_at(const u64 *__restrict__ words, u64 p, int
     return x >> (64 - K);
 }
 
-// element i <-> position p = n-1-i (descending positions: see the end-of-text rule above).
+// Round-0 element generator: element i <-> position p = n-1-i (descending positions: see the
+// end-of-text rule above), key = k-mer of suffix p (<< key_shift, | preceding byte in BWT mode),
+// value = p.  Evaluated by the histogram kernel and by the first digit pass, so the initial
+// (key, position) array is never written or read (saves 30 of ~150 bytes of traffic per suffix).
+struct KmerGen {
+    static const bool kActive = true;
+    const u64 *words; const u8 *text; u64 n; int b, K, key_shift;
+    __device__ __forceinline__ u64 key(u64 i) const
+    {
+        u64 p = n - 1 - i;
+        u64 k = kmer_at(words, p, b, K) << key_shift;
+        if (text != nullptr && p > 0) k |= (u64)text[p - 1];
+        return k;
+    }
+    __device__ __forceinline__ u32 val(u64 i) const { return (u32)(n - 1 - i); }
+};
+
+// Materialising variant (LIBSAIS_CUDA_FUSE_KEYS=0), kept for A/B measurements.
+// element i <-> position p = n-1-i.
 // BWT mode (text != nullptr): the byte preceding the suffix rides in the low 8 key bits,
 // below the sorted bit range, so the BWT falls out of the sort without a gather.
 __global__ void __launch_bounds__(256)
@@ -130,16 +148,21 @@ make_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int K, int key_shi
 }
 
 // ---------------------------------------------------------------------------------------------
-// rank kernel: sorted (key, pos) -> head flags, rank (= slot of the group head), SA / ISA
+// rank stage: sorted (key, pos) -> head flags, rank (= slot of the group head), SA / ISA
 // scatter, compaction of non-singleton ("active") suffixes with their slot and dense group id,
 // and -- for suffixes that became singletons ("final") -- the fused outputs: BWT row byte,
-// primary index, aux samples.
-// One chained scan (decoupled look-back, warp-wide window) over tiles for three quantities:
-//   [0] max : slot of the last group head        [1] sum : active suffixes    [2] sum : active groups
+// primary index, aux samples.  Three kernels, no inter-CTA waiting:
+//   rank_flags  streaming: flags per element as warp ballots (3 words per 32 elements), per-warp
+//               and per-tile aggregates, and everything that needs no prefix: SA[slot], BWT rows,
+//               primary, aux samples
+//   rank_scan   one CTA: exclusive scan of the tile aggregates
+//               [0] max : slot of the last group head   [1] sum : active suffixes   [2] sum : active groups
+//   rank_apply  streaming over the tiles that contain work: rank -> ISA, compaction of the actives
 // ---------------------------------------------------------------------------------------------
 static const int kRankThreads = 256;
 static const int kRankIPT = 8;
 static const int kRankTile = kRankThreads * kRankIPT;
+static const int kRankWarps = kRankThreads / 32;
 static const u32 kIsaInvalid = 0xFFFFFFFFu;
 
 struct RankArgs {
@@ -151,143 +174,234 @@ struct RankArgs {
     u64 aux_mask; int aux_shift; u32 *aux_I;
     u64 *primary;
     u32 *a_pos, *a_slot, *a_grp;
-    u64 *status; u64 ntiles; u32 *ticket; u64 *out_counts; u32 *err;
+    u32 *masks;              // [3][N/32]   head / active / active-head ballots
+    u32 *wagg;               // [ntiles * kRankWarps][3]  per-warp aggregates
+    u32 *tagg;               // [ntiles][3] per-tile aggregates, overwritten by their exclusive scan
+    u64 nchunks;             // ceil(N / 32)
+    u64 ntiles; u64 *out_counts;
 };
-
-// Warp-wide chained scan: all 32 lanes call; lane 0's `agg` is the tile aggregate.  Each round
-// trip inspects 32 predecessors.  Returns the exclusive prefix (all lanes).
-__device__ __forceinline__ u64 chained_scan_warp(u64 *status, u32 tile, u64 agg, bool is_max, u32 *err, int lane)
-{
-    agg = __shfl_sync(0xffffffffu, agg, 0);
-    if (tile == 0) { if (lane == 0) st_relaxed(status, kStFlagInc | agg); return 0; }
-    if (lane == 0) st_relaxed(status + tile, kStFlagAgg | agg);
-    u64 excl = 0;
-    i64 look = (i64)tile - 1;
-    while (true) {
-        i64 idx = look - lane;
-        u64 w = kStFlagInc;                       // before the first tile: an inclusive identity
-        u32 spins = 0;
-        while (true) {
-            if (idx >= 0) w = ld_relaxed(status + idx);
-            if (!__any_sync(0xffffffffu, (w >> 62) == 0)) break;
-            if (++spins > kSpinLimit) { *err = 1; w |= kStFlagInc; break; }
-            __nanosleep(20);
-        }
-        u32 incmask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-        int first = incmask ? (__ffs(incmask) - 1) : 31;
-        u64 v = lane <= first ? (w & kStValMask) : 0;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            u64 o = __shfl_xor_sync(0xffffffffu, v, off);
-            v = is_max ? (o > v ? o : v) : v + o;
-        }
-        excl = is_max ? (v > excl ? v : excl) : excl + v;
-        if (incmask) break;
-        look -= 32;
-    }
-    if (lane == 0) st_relaxed(status + tile, kStFlagInc | (is_max ? (agg > excl ? agg : excl) : excl + agg));
-    return excl;
-}
 
 template <bool ROUND0>
 __global__ void __launch_bounds__(kRankThreads)
-rank_kernel(const RankArgs a)
+rank_flags_kernel(const RankArgs a)
 {
-    constexpr int WARPS = kRankThreads / 32;
-    __shared__ u32 s_tile;
-    __shared__ u64 s_wagg[3][WARPS];     // per-warp aggregates, then exclusive prefixes (incl. tile prefix)
+    __shared__ u32 s_wagg[3][kRankWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const u32 tile = s_tile;
     const u64 N = a.N;
-    const u64 tile_base = (u64)tile * kRankTile;
-    const u64 wbase = tile_base + (u64)warp * (kRankIPT * 32) + lane;
-    const u32 lt = lanemask_lt(), le = lt | (1u << lane);
+    const u64 tile = blockIdx.x;
+    const u64 wbase = tile * kRankTile + (u64)warp * (kRankIPT * 32) + lane;
 
-    u32 p[kRankIPT], slot[kRankIPT], hm[kRankIPT], am[kRankIPT], gm[kRankIPT];
+    // ---- all loads first (independent, latencies overlap).  Neighbours j-1 / j+1 come by shuffle;
+    // only lane 0 of the first item and lane 31 of the last item read across the warp's chunk.
+    u64 kk[kRankIPT]; u32 p[kRankIPT], slot[kRankIPT];
     u32 pc[ROUND0 ? kRankIPT / 4 : 1] = {0};
-    u64 w_head = 0; u32 w_act = 0, w_grp = 0;
 #pragma unroll
     for (int i = 0; i < kRankIPT; ++i) {
-        u64 j = wbase + (u64)i * 32;
-        bool valid = j < N;
-        bool head = false, nexthead = true;
-        p[i] = 0; slot[i] = 0;
+        const u64 j = wbase + (u64)i * 32;
+        const bool valid = j < N;
+        const u64 kraw = valid ? a.keys[j] : 0;
+        kk[i] = kraw >> a.key_shift;
+        p[i] = valid ? a.pos[j] : 0;
+        slot[i] = ROUND0 ? (u32)j : (valid ? a.slot_in[j] : 0);
+        if (ROUND0) pc[i >> 2] |= (u32)(kraw & 255) << (8 * (i & 3));
+    }
+    const u64 jfirst = wbase - lane, jlast = jfirst + kRankIPT * 32;      // chunk = [jfirst, jlast)
+    u64 kbefore = 0, kafter = 0; u32 pbefore = 0, pafter = 0;
+    if (lane == 0 && jfirst > 0 && jfirst < N) { kbefore = a.keys[jfirst - 1] >> a.key_shift; if (ROUND0) pbefore = a.pos[jfirst - 1]; }
+    if (lane == 31 && jlast < N) { kafter = a.keys[jlast] >> a.key_shift; if (ROUND0) pafter = a.pos[jlast]; }
+
+    u32 hm[kRankIPT], tm[ROUND0 ? kRankIPT : 1];
+#pragma unroll
+    for (int i = 0; i < kRankIPT; ++i) {
+        const u64 j = wbase + (u64)i * 32;
+        const bool valid = j < N;
+        u64 kprev = __shfl_up_sync(0xffffffffu, kk[i], 1);
+        const u64 carry = __shfl_sync(0xffffffffu, i ? kk[i ? i - 1 : 0] : kbefore, i ? 31 : 0);   // element j-1 of lane 0
+        if (lane == 0) kprev = carry;
+        hm[i] = __ballot_sync(0xffffffffu, valid && (j == 0 || kprev != kk[i]));
+        if (ROUND0) tm[i] = __ballot_sync(0xffffffffu, valid && (u64)p[i] >= a.tail_start);
+    }
+    // head flag of the element right after the chunk (for the last element's "next head")
+    const bool after_valid = jlast < N;
+    u32 after_head = 1, after_tail = 0, before_tail = 0;
+    {
+        u64 klast = __shfl_sync(0xffffffffu, kk[kRankIPT - 1], 31);
+        after_head = __shfl_sync(0xffffffffu, (u32)(!after_valid || kafter != klast), 31);
+        if (ROUND0) {
+            after_tail = __shfl_sync(0xffffffffu, (u32)(after_valid && (u64)pafter >= a.tail_start), 31);
+            before_tail = __shfl_sync(0xffffffffu, (u32)(jfirst > 0 && jfirst < N && (u64)pbefore >= a.tail_start), 0);
+        }
+    }
+    u32 vmask[kRankIPT];
+#pragma unroll
+    for (int i = 0; i < kRankIPT; ++i) vmask[i] = __ballot_sync(0xffffffffu, wbase + (u64)i * 32 < N);
+    if (ROUND0) {
+        // tail suffixes are singletons: they are heads, and so is the element after one
+#pragma unroll
+        for (int i = 0; i < kRankIPT; ++i) {
+            u32 prev_tail = (tm[i] << 1) | (i ? (tm[i ? i - 1 : 0] >> 31) : before_tail);
+            hm[i] |= tm[i] | (prev_tail & vmask[i]);
+        }
+        after_head |= after_tail | (tm[kRankIPT - 1] >> 31);
+    }
+    u32 w_head = 0, w_act = 0, w_grp = 0;
+#pragma unroll
+    for (int i = 0; i < kRankIPT; ++i) {
+        const u64 j = wbase + (u64)i * 32;
+        const bool valid = j < N;
+        const u32 vm = vmask[i];
+        // next-head mask: head flag of element j+1; an element beyond N counts as a head
+        const u32 nh_in = (hm[i] >> 1) | ((i + 1 < kRankIPT ? (hm[i + 1 < kRankIPT ? i + 1 : 0] & 1u) : after_head) << 31);
+        const u32 nv = (vm >> 1) | ((i + 1 < kRankIPT ? (vmask[i + 1 < kRankIPT ? i + 1 : 0] & 1u) : (u32)after_valid) << 31);
+        const u32 nh = nh_in | ~nv;
+        const u32 am = vm & ~(hm[i] & nh);
+        const u32 gm = am & hm[i];
+        if (hm[i]) w_head = __shfl_sync(0xffffffffu, slot[i], 31 - __clz(hm[i]));   // slots ascend: the latest head wins
+        w_act += __popc(am);
+        w_grp += __popc(gm);
+        const u64 chunk = j >> 5;
+        if (lane == 0 && chunk < a.nchunks) {
+            a.masks[chunk] = hm[i]; a.masks[a.nchunks + chunk] = am; a.masks[2 * a.nchunks + chunk] = gm;
+        }
         if (valid) {
-            u64 kraw = a.keys[j];
-            u64 k = kraw >> a.key_shift;
-            p[i] = a.pos[j];
-            slot[i] = ROUND0 ? (u32)j : a.slot_in[j];
-            if (ROUND0) pc[i >> 2] |= (u32)(kraw & 255) << (8 * (i & 3));
-            head = (j == 0) || ((a.keys[j - 1] >> a.key_shift) != k);
-            nexthead = (j + 1 == N) || ((a.keys[j + 1] >> a.key_shift) != k);
-            if (ROUND0) {
-                bool tail = (u64)p[i] >= a.tail_start;
-                head = head || tail || (j != 0 && (u64)a.pos[j - (j ? 1 : 0)] >= a.tail_start);
-                nexthead = nexthead || tail || (j + 1 < N && (u64)a.pos[j + 1] >= a.tail_start);
-            }
-        }
-        bool active = valid && !(head && nexthead);
-        hm[i] = __ballot_sync(0xffffffffu, head);
-        am[i] = __ballot_sync(0xffffffffu, active);
-        gm[i] = __ballot_sync(0xffffffffu, active && head);
-        if (hm[i]) {
-            u32 src = 31 - __clz(hm[i]);
-            w_head = (u64)__shfl_sync(0xffffffffu, slot[i], src);   // slots ascend: the latest head wins
-        }
-        w_act += __popc(am[i]);
-        w_grp += __popc(gm[i]);
-    }
-    if (lane == 0) { s_wagg[0][warp] = w_head; s_wagg[1][warp] = w_act; s_wagg[2][warp] = w_grp; }
-    __syncthreads();
-
-    // warps 0..2 each scan one quantity: over the block's warps (lanes 0..WARPS-1), then over the tiles
-    if (warp < 3) {
-        const bool is_max = warp == 0;
-        u64 mine = lane < WARPS ? s_wagg[warp][lane] : 0;
-        u64 inc = mine;
-#pragma unroll
-        for (int off = 1; off < WARPS; off <<= 1) {
-            u64 o = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane >= off) inc = is_max ? (o > inc ? o : inc) : inc + o;
-        }
-        u64 ex = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) ex = 0;
-        u64 total = __shfl_sync(0xffffffffu, inc, WARPS - 1);
-        u64 excl = chained_scan_warp(a.status + (u64)warp * a.ntiles, tile, total, is_max, a.err, lane);
-        if (lane < WARPS) s_wagg[warp][lane] = is_max ? (ex > excl ? ex : excl) : ex + excl;
-        if (tile + 1 == a.ntiles && !is_max && lane == 0) a.out_counts[warp - 1] = excl + total;
-    }
-    __syncthreads();
-
-    u32 c_head = (u32)s_wagg[0][warp];
-    u32 c_act = (u32)s_wagg[1][warp];
-    u32 c_grp = (u32)s_wagg[2][warp];
-#pragma unroll
-    for (int i = 0; i < kRankIPT; ++i) {
-        u64 j = wbase + (u64)i * 32;
-        u32 hle = hm[i] & le;
-        u32 src = hle ? (31 - __clz(hle)) : 0;
-        u32 hs = __shfl_sync(0xffffffffu, slot[i], src);
-        u32 rank = hle ? hs : c_head;
-        if (j < N) {
-            const bool act = (am[i] >> lane) & 1;
+            const bool act = (am >> lane) & 1;
             if (a.SA) a.SA[slot[i]] = p[i];
-            if (a.isa_all || act) a.ISA[p[i]] = rank;
             if (a.rows) {
                 if (ROUND0) a.rows[slot[i]] = (u8)(pc[i >> 2] >> (8 * (i & 3)));
                 else if (!act && p[i] != 0) a.rows[slot[i]] = a.text[p[i] - 1];
             }
-            if (act) {
-                u32 o = c_act + __popc(am[i] & lt);
-                a.a_pos[o] = p[i];
-                a.a_slot[o] = slot[i];
-                a.a_grp[o] = c_grp + __popc(gm[i] & le) - 1;
-            } else {
+            if (!act) {
                 // final: this suffix's slot will never change again
                 if (p[i] == 0) *a.primary = (u64)slot[i] + 1;
                 if (a.aux_I && ((u64)p[i] & a.aux_mask) == 0) a.aux_I[p[i] >> a.aux_shift] = slot[i] + 1;
+            }
+        }
+    }
+    if (lane == 0) {
+        u32 *wa = a.wagg + (tile * kRankWarps + warp) * 3;
+        wa[0] = w_head; wa[1] = w_act; wa[2] = w_grp;
+        s_wagg[0][warp] = w_head; s_wagg[1][warp] = w_act; s_wagg[2][warp] = w_grp;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        u32 r = 0;
+#pragma unroll
+        for (int w = 0; w < kRankWarps; ++w) { u32 v = s_wagg[tid][w]; r = tid == 0 ? (v > r ? v : r) : r + v; }
+        a.tagg[(u64)tid * a.ntiles + tile] = r;
+    }
+}
+
+// One CTA: exclusive scan of the tile aggregates in place (SoA: tagg[q * ntiles + tile]);
+// totals -> out_counts[0..1].  Each warp owns a contiguous segment of tiles and walks it 32
+// tiles at a time (coalesced loads, shuffle scan, running carry): reduce, combine, re-walk.
+__device__ __forceinline__ u32 warp_incl_scan(u32 v, bool is_max, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        u32 o = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v = is_max ? (o > v ? o : v) : v + o;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(1024)
+rank_scan_kernel(u32 *__restrict__ tagg, u64 ntiles, u64 *__restrict__ out_counts)
+{
+    __shared__ u32 s_tot[3][32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u64 per = ((ntiles + 31) / 32 + 31) / 32 * 32;          // tiles per warp, multiple of 32
+    const u64 lo = (u64)warp * per, hi = lo + per < ntiles ? lo + per : ntiles;
+    for (int q = 0; q < 3; ++q) {
+        const bool is_max = q == 0;
+        u32 r = 0;
+        for (u64 i = lo + lane; i < hi; i += 32) { u32 v = tagg[q * ntiles + i]; r = is_max ? (v > r ? v : r) : r + v; }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { u32 o = __shfl_xor_sync(0xffffffffu, r, off); r = is_max ? (o > r ? o : r) : r + o; }
+        if (lane == 0) s_tot[q][warp] = r;
+    }
+    __syncthreads();
+    if (warp < 3) {
+        const bool is_max = warp == 0;
+        u32 v = s_tot[warp][lane];
+        u32 inc = warp_incl_scan(v, is_max, lane);
+        u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = 0;
+        s_tot[warp][lane] = ex;
+        if (lane == 31 && !is_max) out_counts[warp - 1] = inc;
+    }
+    __syncthreads();
+    for (int q = 0; q < 3; ++q) {
+        const bool is_max = q == 0;
+        u32 carry = s_tot[q][warp];
+        for (u64 base = lo; base < hi; base += 32) {
+            const u64 i = base + lane;
+            u32 v = i < hi ? tagg[q * ntiles + i] : 0;
+            u32 inc = warp_incl_scan(v, is_max, lane);
+            u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) ex = 0;
+            ex = is_max ? (ex > carry ? ex : carry) : ex + carry;
+            if (i < hi) tagg[q * ntiles + i] = ex;
+            u32 tot = __shfl_sync(0xffffffffu, inc, 31);
+            carry = is_max ? (tot > carry ? tot : carry) : carry + tot;
+        }
+    }
+}
+
+template <bool ROUND0>
+__global__ void __launch_bounds__(kRankThreads)
+rank_apply_kernel(const RankArgs a)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 N = a.N;
+    const u64 tile = blockIdx.x;
+    // tiles without active suffixes have nothing to do unless every rank is wanted
+    u32 t_head = a.tagg[tile], t_act = a.tagg[a.ntiles + tile], t_grp = a.tagg[2 * a.ntiles + tile];
+    if (!a.isa_all) {
+        const u32 next_act = tile + 1 < a.ntiles ? a.tagg[a.ntiles + tile + 1] : (u32)a.out_counts[0];
+        if (next_act == t_act) return;
+    }
+    // exclusive prefix of this warp inside the tile from the per-warp aggregates
+    u32 c_head = t_head, c_act = t_act, c_grp = t_grp;
+    {
+        const u32 *wa = a.wagg + tile * kRankWarps * 3;
+        u32 h = lane < warp ? wa[lane * 3] : 0, x = lane < warp ? wa[lane * 3 + 1] : 0, g = lane < warp ? wa[lane * 3 + 2] : 0;
+#pragma unroll
+        for (int off = 4; off; off >>= 1) {
+            u32 oh = __shfl_xor_sync(0xffffffffu, h, off); h = oh > h ? oh : h;
+            x += __shfl_xor_sync(0xffffffffu, x, off);
+            g += __shfl_xor_sync(0xffffffffu, g, off);
+        }
+        h = __shfl_sync(0xffffffffu, h, 0); x = __shfl_sync(0xffffffffu, x, 0); g = __shfl_sync(0xffffffffu, g, 0);
+        c_head = h > c_head ? h : c_head; c_act += x; c_grp += g;
+    }
+    const u64 wbase = tile * kRankTile + (u64)warp * (kRankIPT * 32) + lane;
+    const u32 lt = lanemask_lt(), le = lt | (1u << lane);
+    u32 p[kRankIPT], slot[kRankIPT], hm[kRankIPT], am[kRankIPT], gm[kRankIPT];
+#pragma unroll
+    for (int i = 0; i < kRankIPT; ++i) {
+        const u64 j = wbase + (u64)i * 32;
+        const bool valid = j < N;
+        const u64 chunk = j >> 5;
+        const bool cv = chunk < a.nchunks;
+        hm[i] = cv ? a.masks[chunk] : 0; am[i] = cv ? a.masks[a.nchunks + chunk] : 0; gm[i] = cv ? a.masks[2 * a.nchunks + chunk] : 0;
+        p[i] = valid ? a.pos[j] : 0;
+        slot[i] = ROUND0 ? (u32)j : (valid ? a.slot_in[j] : 0);
+    }
+#pragma unroll
+    for (int i = 0; i < kRankIPT; ++i) {
+        const u64 j = wbase + (u64)i * 32;
+        const u32 hle = hm[i] & le;
+        const u32 src = hle ? (31 - __clz(hle)) : 0;
+        const u32 hs = __shfl_sync(0xffffffffu, slot[i], src);
+        const u32 rank = hle ? hs : c_head;
+        if (j < N) {
+            const bool act = (am[i] >> lane) & 1;
+            if (a.isa_all || act) a.ISA[p[i]] = rank;
+            if (act) {
+                const u32 o = c_act + __popc(am[i] & lt);
+                a.a_pos[o] = p[i];
+                a.a_slot[o] = slot[i];
+                a.a_grp[o] = c_grp + __popc(gm[i] & le) - 1;
             }
         }
         if (hm[i]) c_head = __shfl_sync(0xffffffffu, slot[i], 31 - __clz(hm[i]));
@@ -361,7 +475,7 @@ size_t sa_workspace_bytes(u64 n, int sym_bytes)
                               + 4 + 4            /* SA, ISA */
                               + 4 + 4 + 4 + 4    /* a_pos, a_grp, a_slot x2 */
                               + 1);              /* lazy mode: separate small round buffers */
-    size_t st = 3 * ceil_div(n, kRankTile) * sizeof(u64);
+    size_t st = 3 * ceil_div(n, 32) * sizeof(u32) + ceil_div(n, kRankTile) * (kRankWarps + 1) * 3 * sizeof(u32) + 1024;
     return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + 256 + 32 * 256 + 4096;
 }
 
@@ -445,11 +559,12 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     u32 *a_pos = c.alloc_n<u32>(n), *a_grp = c.alloc_n<u32>(n);
     u32 *a_slot0 = c.alloc_n<u32>(n), *a_slot1 = c.alloc_n<u32>(n);
     const u64 rank_tiles = ceil_div(n, kRankTile);
-    u64 *rstatus = c.alloc_n<u64>(3 * rank_tiles);
+    u32 *rmasks = c.alloc_n<u32>(3 * ceil_div(n, 32));
+    u32 *rwagg = c.alloc_n<u32>(rank_tiles * kRankWarps * 3);
+    u32 *rtagg = c.alloc_n<u32>(rank_tiles * 3);
     void *sort_temp = c.alloc(RadixSort<u64, u32>::temp_bytes(n));
-    if (!sort_temp || !rstatus || !a_slot1 || (opt.want_sa && !SA)) return -2;
+    if (!sort_temp || !rmasks || !rwagg || !rtagg || !a_slot1 || (opt.want_sa && !SA)) return -2;
     u32 *err = (u32 *)(c.d_scalars + S_ERR);
-    u32 *tickets = (u32 *)(c.d_scalars + S_TICKET);
     c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, (S_MISC - S_ERR) * sizeof(u64), st));
     c.check(cudaMemsetAsync(ISA, 0xFF, n * sizeof(u32), st));                  // kIsaInvalid everywhere
 
@@ -460,13 +575,21 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         if (sym_bytes == 1) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u8, true>), grid, 256, 0, (const u8 *)d_T, n, b, words, nwords, d_lut);
         else if (sym_bytes == 4) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u32, false>), grid, 256, 0, (const u32 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
         else LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u64, false>), grid, 256, 0, (const u64 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
-        LSC_LAUNCH(c, KC_MAKE_KEYS, (double)nwords * 8 + (double)n * (12 + (bwt_mode ? 1 : 0)), make_keys_kernel,
-                   (u32)ceil_div(n, 256), 256, 0, words, n, b, K, key_shift, bwt_mode ? (const u8 *)d_T : (const u8 *)nullptr, keyA, valA);
     }
 
     // ---- round 0: sort by the k-mer, rank, compact
     RoundStat rs; rs.h = 0; rs.n_active = n; rs.key_bits = K; rs.passes = 0; rs.n_groups = 0;
-    int where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, n, key_shift, key_shift + K, sort_temp, err, &rs.passes);
+    bool fuse_keys = true;
+    { const char *env = getenv("LIBSAIS_CUDA_FUSE_KEYS"); if (env && *env) fuse_keys = atoi(env) != 0; }
+    int where;
+    if (fuse_keys) {
+        KmerGen gen; gen.words = words; gen.text = bwt_mode ? (const u8 *)d_T : nullptr; gen.n = n; gen.b = b; gen.K = K; gen.key_shift = key_shift;
+        where = RadixSort<u64, u32>::sort_from<KmerGen>(c, gen, keyA, valA, keyB, valB, n, key_shift, key_shift + K, sort_temp, err, &rs.passes);
+    } else {
+        LSC_LAUNCH(c, KC_MAKE_KEYS, (double)nwords * 8 + (double)n * (12 + (bwt_mode ? 1 : 0)), make_keys_kernel,
+                   (u32)ceil_div(n, 256), 256, 0, words, n, b, K, key_shift, bwt_mode ? (const u8 *)d_T : (const u8 *)nullptr, keyA, valA);
+        where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, n, key_shift, key_shift + K, sort_temp, err, &rs.passes);
+    }
     if (where < 0) return -2;
     u64 *ks = where ? keyB : keyA; u32 *vs = where ? valB : valA;      // S0: sorted round-0 (key, pos)
     u64 *ko = where ? keyA : keyB; u32 *vo = where ? valA : valB;
@@ -480,9 +603,11 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     ra.aux_I = opt.aux_I; ra.aux_mask = opt.aux_I ? opt.aux_r - 1 : 0; ra.aux_shift = opt.aux_I ? bits_for(opt.aux_r) - 1 : 0;
     ra.primary = c.d_scalars + S_PRIMARY;
     ra.a_pos = a_pos; ra.a_slot = slot_cur; ra.a_grp = a_grp;
-    ra.status = rstatus; ra.ntiles = rank_tiles; ra.ticket = tickets + 0; ra.out_counts = c.d_scalars + S_NACT; ra.err = err;
-    c.check(cudaMemsetAsync(rstatus, 0, 3 * rank_tiles * sizeof(u64), st));
-    LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+    ra.masks = rmasks; ra.wagg = rwagg; ra.tagg = rtagg; ra.nchunks = ceil_div(n, 32);
+    ra.ntiles = rank_tiles; ra.out_counts = c.d_scalars + S_NACT;
+    LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+    LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, 1, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
+    LSC_LAUNCH(c, KC_RANK_INIT, 0.0, rank_apply_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
     if (!read_round_scalars(c)) return -2;
     u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
     rs.n_groups = G;
@@ -522,11 +647,11 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         where = RadixSort<u64, u32>::sort(c, rk0, rv0, rk1, rv1, N, 0, rank_bits + grp_bits, sort_temp, err, &r.passes);
         if (where < 0) return -2;
         const u64 tiles = ceil_div(N, kRankTile);
-        c.check(cudaMemsetAsync(rstatus, 0, 3 * rank_tiles * sizeof(u64), st));
-        c.check(cudaMemsetAsync(tickets + (round & 7), 0, sizeof(u32), st));
         ra.keys = where ? rk1 : rk0; ra.pos = where ? rv1 : rv0; ra.slot_in = slot_cur; ra.N = N; ra.tail_start = 0; ra.key_shift = 0;
-        ra.isa_all = 1; ra.a_slot = slot_nxt; ra.ntiles = tiles; ra.ticket = tickets + (round & 7);
-        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 8), rank_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        ra.isa_all = 1; ra.a_slot = slot_nxt; ra.ntiles = tiles; ra.nchunks = ceil_div(N, 32);
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 4), rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, 1, 1024, 0, rtagg, tiles, c.d_scalars + S_NACT);
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (4 + 4 + 4 + 12), rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
         if (!read_round_scalars(c)) return -2;
         N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
         r.n_groups = G;
