@@ -45,13 +45,14 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons; samples are kept only if they fall inside the timed
+    region [mark_start(), mark_stop()] (nvidia-smi needs a moment to start, so it is launched early)."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.lines, self.proc = [], None
+        self.lines, self.proc, self.t0, self.t1 = [], None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -60,28 +61,38 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for l in self.lines:
+        sm, mx, reasons, allsm = [], 0, set(), []
+        for ts, l in self.lines:
             f = [x.strip() for x in l.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                v = float(f[1]); mx = max(mx, float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
+            allsm.append(v)
+            if self.t0 is not None and not (self.t0 - 0.02 <= ts <= (self.t1 or ts) + 0.05):
+                continue
+            sm.append(v)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
                     reasons.add(name)
-        busy = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        use = sm if sm else allsm
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_total": len(allsm)}
 
 
 def ref_lib():
@@ -162,7 +173,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--n", type=int, default=N_FULL, help="text bytes per GPU per step (default: the 256 MiB config)")
@@ -210,13 +221,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm
+    sampler = ClockSampler(local) if rank == 0 else None
     ctx.set_profiling(not args.no_profile)
     primary = None
     for _ in range(args.warmup):
         primary = ctx.bwt_dev(dT.data_ptr(), dU.data_ptr(), n)
         assert primary > 0, "bwt_dev failed: %d (cuda error %d)" % (primary, ctx.last_error())
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     agg = {}
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,6 +245,8 @@ def main():
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
+    if sampler:
+        sampler.mark_stop()
     clocks = sampler.stop() if sampler else None
     rounds = ctx.stats()["rounds"]
 

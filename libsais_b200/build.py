@@ -14,7 +14,8 @@ OUT = os.path.join(HERE, "libsais_cuda.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["ctx.cu", "sa_core.cu", "post.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+EXTRA = os.environ.get("LSC_NVCC_EXTRA", "").split()
+FLAGS = EXTRA + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v" if os.environ.get("LSC_PTXAS_V") else "-O3",
          "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
 

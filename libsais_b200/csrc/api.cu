@@ -416,6 +416,17 @@ int32_t libsais_cuda_get_round(const void *ctx, int32_t round, libsais_cuda_roun
     return 0;
 }
 const char *libsais_cuda_kernel_class_name(int32_t kc) { return kc >= 0 && kc < KC_COUNT ? kKernelClassName[kc] : ""; }
+// debug: raw device scalars S_ERR.. (look-back statistics when built with -DLSC_LOOKBACK_STATS)
+int32_t libsais_cuda_debug_scalars(const void *ctx, uint32_t *out, int32_t count)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !out || count < 0 || count > 16) return -1;
+    DeviceGuard g(c->device);
+    // counters live at u32 offset 112 from S_ERR (= u64 slot S_ERR + 56); read and clear
+    u64 *p = c->d_scalars + S_ERR + 56;
+    if (cudaMemcpy(out, p, count * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    return cudaMemset(p, 0, 16 * sizeof(uint32_t)) == cudaSuccess ? 0 : -2;
+}
 int32_t libsais_cuda_last_error(const void *ctx) { Ctx *c = ctx ? as_ctx(ctx) : default_ctx(); return c ? (int32_t)c->last_error : -1; }
 
 int64_t libsais_cuda_sa_dev(const void *ctx, const uint8_t *d_T, uint32_t *d_SA, int64_t n)

@@ -26,6 +26,7 @@ enum KernelClass {
     KC_SORT_HIST,      // onesweep upfront digit histograms
     KC_SORT_SCAN,      // digit-base exclusive scan
     KC_SORT_PASS,      // onesweep digit pass (the dominant kernel)
+    KC_SORT_PASS_GEN,  // first digit pass fused with k-mer key generation (reads the packed text, not a key array)
     KC_RANK_INIT,      // round-0 head flags + rank + ISA scatter + compaction
     KC_RANK_SCAN,      // scan of the rank stage's tile aggregates
     KC_ROUND_KEYS,     // round>=1 key build (ISA gather)
@@ -43,7 +44,7 @@ enum KernelClass {
 };
 
 static const char *const kKernelClassName[KC_COUNT] = {
-    "hist_sym", "pack", "make_keys", "sort_hist", "sort_scan", "sort_pass", "rank_init", "rank_scan",
+    "hist_sym", "pack", "make_keys", "sort_hist", "sort_scan", "sort_pass", "sort_pass_gen", "rank_init", "rank_scan",
     "round_keys", "rank_update", "small_sort", "bwt", "phi", "plcp", "lcp",
     "unbwt_prep", "unbwt_walk", "unbwt_rank", "convert"
 };
@@ -60,6 +61,16 @@ __device__ __forceinline__ u64 ld_relaxed(const u64 *p)
 __device__ __forceinline__ void st_relaxed(u64 *p, u64 v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u32 ld_relaxed(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u32 *p, u32 v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ u32 lanemask_lt()
 {

@@ -20,9 +20,16 @@ static const int kRadixBits = 8;
 static const int kRadixSize = 256;
 static const int kMaxPasses = 16;
 
-static const u64 kStFlagAgg  = 1ull << 62;   // tile aggregate published
-static const u64 kStFlagInc  = 2ull << 62;   // inclusive prefix published
-static const u64 kStValMask  = (1ull << 62) - 1;
+// Tile status word of the chained scan: 2 flag bits (0 = not published, 1 = tile aggregate,
+// 2 = inclusive prefix) above the count.  u32 words (30-bit counts) when n < 2^30 -- half the
+// look-back traffic -- else u64.
+template <typename ST> struct StWord {
+    static const int kShift = (int)sizeof(ST) * 8 - 2;
+    __host__ __device__ static ST agg(u64 v) { return (ST)(((ST)1 << kShift) | (ST)v); }
+    __host__ __device__ static ST inc(u64 v) { return (ST)(((ST)2 << kShift) | (ST)v); }
+    __host__ __device__ static u32 flag(ST w) { return (u32)(w >> kShift); }
+    __host__ __device__ static u64 val(ST w) { return (u64)(w & ((((ST)1) << kShift) - 1)); }
+};
 static const u32 kSpinLimit  = 1u << 27;     // look-back watchdog: flag an error instead of hanging the GPU
 
 struct SortPlan {
@@ -143,50 +150,71 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-static const int kLookBatch = 8;           // predecessor status words fetched per look-back round trip
+static const int kLookBatch = 8;           // predecessor status words prefetched before the ranking
+static const int kLookRefill = 16;         // words per further round trip
 
-// Exclusive prefix of this tile's digit count over all earlier tiles (decoupled look-back).
-// The predecessors' status words are fetched kLookBatch at a time so one L2 round trip
-// covers several tiles; a word that is not published yet is polled individually.
-__device__ __forceinline__ u64 lookback_digit(u64 *status, u32 tile, u32 digit, u32 cnt, u32 *err)
+// Decoupled look-back for one digit, split in two so the first round trip overlaps the ranking:
+// lookback_prefetch() issues the loads of the kLookBatch nearest predecessors' status words right
+// after this tile published its counts; lookback_finish() consumes them (by then they have
+// arrived), polls words that were not published yet, and continues further back if needed
+// (measured on B200, 2 x 148 tiles in flight: the nearest inclusive prefix is ~22 tiles back).
+template <typename ST> struct LookState { ST w[kLookBatch]; };
+
+template <typename ST>
+__device__ __forceinline__ void lookback_prefetch(LookState<ST> &ls, const ST *status, u32 tile, u32 digit)
 {
-    u64 *mine = status + (u64)tile * kRadixSize + digit;
+#pragma unroll
+    for (int j = 0; j < kLookBatch; ++j) {
+        i64 idx = (i64)tile - 1 - j;
+        ls.w[j] = idx >= 0 ? ld_relaxed(status + (u64)idx * kRadixSize + digit) : StWord<ST>::inc(0);
+    }
+}
+
+// One status word of a predecessor tile: poll until published, accumulate; true when it carried
+// an inclusive prefix (the look-back is complete).
+template <typename ST>
+__device__ __forceinline__ bool lookback_consume(ST x, const ST *status, i64 idx, u32 digit, u64 &excl, u32 *err)
+{
+    u32 spins = 0;
+    while (StWord<ST>::flag(x) == 0) {
+        if (++spins > kSpinLimit) { *err = 1; x = StWord<ST>::inc(0); break; }
+        __nanosleep(20);
+        x = ld_relaxed(status + (u64)idx * kRadixSize + digit);
+    }
+    excl += StWord<ST>::val(x);
+    return StWord<ST>::flag(x) == 2;
+}
+
+template <typename ST>
+__device__ __forceinline__ u64 lookback_finish(LookState<ST> &ls, ST *status, u32 tile, u32 digit, u32 cnt, u32 *err)
+{
     if (tile == 0) return 0;
     u64 excl = 0;
     i64 look = (i64)tile - 1;
     bool done = false;
+#pragma unroll
+    for (int j = 0; j < kLookBatch; ++j)
+        if (!done) done = lookback_consume<ST>(ls.w[j], status, look - j, digit, excl, err);
+    look -= kLookBatch;
     while (!done) {
-        u64 w[kLookBatch];
+        ST w[kLookRefill];
 #pragma unroll
-        for (int j = 0; j < kLookBatch; ++j) {
+        for (int j = 0; j < kLookRefill; ++j) {
             i64 idx = look - j;
-            w[j] = idx >= 0 ? ld_relaxed(status + (u64)idx * kRadixSize + digit) : kStFlagInc;
+            w[j] = idx >= 0 ? ld_relaxed(status + (u64)idx * kRadixSize + digit) : StWord<ST>::inc(0);
         }
 #pragma unroll
-        for (int j = 0; j < kLookBatch; ++j) {
-            if (!done) {
-                u64 x = w[j];
-                u32 spins = 0;
-                while ((x >> 62) == 0) {
-                    if (++spins > kSpinLimit) { *err = 1; x = kStFlagInc; break; }
-                    __nanosleep(20);
-                    x = ld_relaxed(status + (u64)(look - j) * kRadixSize + digit);
-                }
-                excl += x & kStValMask;
-                if ((x >> 62) == 2) done = true;
-            }
-        }
-        look -= kLookBatch;
+        for (int j = 0; j < kLookRefill; ++j)
+            if (!done) done = lookback_consume<ST>(w[j], status, look - j, digit, excl, err);
+        look -= kLookRefill;
     }
-    st_relaxed(mine, kStFlagInc | (excl + (u64)cnt));
+    st_relaxed(status + (u64)tile * kRadixSize + digit, StWord<ST>::inc(excl + (u64)cnt));
     return excl;
 }
 
-// peers of this lane: lanes whose (valid) item has the same digit
-template <bool USE_MATCH>
+// peers of this lane: lanes whose (valid) item has the same digit -- AND over one ballot per digit bit
 __device__ __forceinline__ u32 digit_peers(u32 d, bool valid, int lane)
 {
-    if (USE_MATCH) return __match_any_sync(0xffffffffu, d);        // invalid items carry d = 256: their own class
     u32 peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
     for (int bit = 0; bit < kRadixBits; ++bit) {
@@ -197,12 +225,12 @@ __device__ __forceinline__ u32 digit_peers(u32 d, bool valid, int lane)
     return valid ? peers : (1u << lane);
 }
 
-template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, int NMATCH, bool FULL, typename Gen>
+template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, typename ST, bool FULL, typename Gen>
 __device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT, VALS> &sm, const Gen &gen,
                                                const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
                                                KeyT *__restrict__ kout, ValT *__restrict__ vout,
                                                const u32 tile, const u32 count, int shift, u32 dmask,
-                                               const u64 *__restrict__ base, u64 *status, u32 *err)
+                                               const u64 *__restrict__ base, ST *status, u32 *err)
 {
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * IPT;
@@ -235,67 +263,81 @@ __device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT
         }
     }
 
-    // ---- counting pre-pass: the tile's digit counts, published before the (longer) ranking phase
+    // ---- counting pre-pass: digit counts of every warp (warp-private shared counters)
+    u32 *wh = sm.whist + warp * kRadixSize;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 li = wbase + i * 32;
-        if (FULL || li < count) atomicAdd(&sm.cnt[digit_of(key[i], shift, dmask)], 1u);
+        if (FULL || li < count) atomicAdd(&wh[digit_of(key[i], shift, dmask)], 1u);
     }
     __syncthreads();
+
+    // ---- per digit: tile count -> publish EARLY (before the long ranking phase), prefetch the
+    // look-back, offsets of every (warp, digit) run inside the tile
     u32 cnt = 0, tileoff = 0;
+    u64 gbase = 0;
+    LookState<ST> ls;
     if (tid < kRadixSize) {
-        cnt = sm.cnt[tid];
-        st_relaxed(status + (u64)tile * kRadixSize + tid, (tile == 0 ? kStFlagInc : kStFlagAgg) | (u64)cnt);
-        // exclusive scan of the 256 counts: warp scan + totals of the 8 digit warps
+        gbase = base[tid];
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) cnt += sm.whist[w * kRadixSize + tid];
+        st_relaxed(status + (u64)tile * kRadixSize + tid, tile == 0 ? StWord<ST>::inc(cnt) : StWord<ST>::agg(cnt));
+        lookback_prefetch<ST>(ls, status, tile, (u32)tid);
         u32 x = cnt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
         if (lane == 31) sm.scan_tmp[warp] = x;
         tileoff = x - cnt;
     }
+    __syncthreads();
+    if (tid < kRadixSize) {
+#pragma unroll
+        for (int w = 0; w < kRadixSize / 32; ++w) if (w < warp) tileoff += sm.scan_tmp[w];
+        u32 run = tileoff;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { u32 t = sm.whist[w * kRadixSize + tid]; sm.whist[w * kRadixSize + tid] = run; run += t; }
+    }
+    __syncthreads();
 
-    // ---- warp-level multisplit: rank of every item among the items of its warp with the same digit
-    u32 rnk[IPT];
-    u32 *wh = sm.whist + warp * kRadixSize;
+    // ---- warp-level multisplit + scatter into shared memory in sorted order: the group leader
+    // claims the run's next slots with one shared atomic (returns the group's base), every lane
+    // adds its rank inside the group.  Items of a warp are claimed in program order -> stable.
     const u32 lt = lanemask_lt();
+    constexpr bool STASH_IN_KEY = sizeof(KeyT) >= 4;       // the slot of a cp.async value rides in the dead key register
+    u32 spos[(VALS == 2 && !STASH_IN_KEY) ? IPT : 1];
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 li = wbase + i * 32;
         bool valid = FULL || li < count;
         u32 d = valid ? digit_of(key[i], shift, dmask) : (u32)kRadixSize;
-        u32 peers = (i < NMATCH) ? digit_peers<true>(d, valid, lane) : digit_peers<false>(d, valid, lane);
+        u32 peers = digit_peers(d, valid, lane);
         int leader = __ffs(peers) - 1;
-        u32 old = 0;
-        if (lane == leader && valid) { old = wh[d]; wh[d] = old + __popc(peers); }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rnk[i] = old + __popc(peers & lt);
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- per digit: offsets of every warp's run inside the tile, then the chained scan over tiles
-    if (tid < kRadixSize) {
-#pragma unroll
-        for (int w = 0; w < kRadixSize / 32; ++w) if (w < warp) tileoff += sm.scan_tmp[w];
-        u32 sum = tileoff;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) { u32 t = sm.whist[w * kRadixSize + tid]; sm.whist[w * kRadixSize + tid] = sum; sum += t; }
-        u64 excl = lookback_digit(status, tile, (u32)tid, cnt, err);
-        sm.goff[tid] = base[tid] + excl - (u64)tileoff;
-    }
-    if (VALS == 2 && !Gen::kActive) cp_async_wait_all();
-    __syncthreads();
-
-    // ---- scatter keys and values into their place inside the tile (shared memory)
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        u32 li = wbase + i * 32;
-        if (FULL || li < count) {
-            u32 pos = wh[digit_of(key[i], shift, dmask)] + rnk[i];
+        u32 basepos = 0;
+        if (lane == leader && valid) basepos = atomicAdd(&wh[d], (u32)__popc(peers));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (valid) {
+            u32 pos = basepos + __popc(peers & lt);
             sm.keys[pos] = key[i];
-            sm.vals[pos] = Gen::kActive ? (ValT)gen.val(tile_base + li)
-                                        : (VALS == 1 ? val[VALS == 1 ? i : 0] : sm.vals_in[VALS == 2 ? li : 0]);
+            if (Gen::kActive) sm.vals[pos] = (ValT)gen.val(tile_base + li);
+            else if (VALS == 1) sm.vals[pos] = val[VALS == 1 ? i : 0];
+            else if (STASH_IN_KEY) key[i] = (KeyT)pos;    // remember the slot for the value (cp.async still in flight)
+            else spos[(VALS == 2 && !STASH_IN_KEY) ? i : 0] = pos;
         }
+    }
+    if (VALS == 2 && !Gen::kActive) {
+        cp_async_wait_all();
+        __syncwarp();                                 // a warp reads only the values it fetched itself
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            u32 li = wbase + i * 32;
+            if (FULL || li < count) sm.vals[STASH_IN_KEY ? (u32)key[i] : spos[(VALS == 2 && !STASH_IN_KEY) ? i : 0]] = sm.vals_in[VALS == 2 ? li : 0];
+        }
+    }
+
+    // ---- chained scan over tiles (first round trip was prefetched before the ranking)
+    if (tid < kRadixSize) {
+        u64 excl = lookback_finish<ST>(ls, status, tile, (u32)tid, cnt, err);
+        sm.goff[tid] = gbase + excl - (u64)tileoff;
     }
     __syncthreads();
 
@@ -312,12 +354,12 @@ __device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT
     }
 }
 
-template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, int NMATCH, typename Gen>
+template <typename KeyT, typename ValT, int THREADS, int IPT, int VALS, typename ST, typename Gen>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : (THREADS <= 512 ? 2 : 1)))
 sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
                  KeyT *__restrict__ kout, ValT *__restrict__ vout, u64 n,
                  int shift, u32 dmask, const u64 *__restrict__ base,
-                 u64 *status, u32 *ticket, u32 *err, const Gen gen)
+                 ST *status, u32 *ticket, u32 *err, const Gen gen)
 {
     typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
     constexpr int WARPS = THREADS / 32;
@@ -338,9 +380,9 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     const u64 tile_base = (u64)tile * TILE;
     const u32 count = (u32)((n - tile_base) < (u64)TILE ? (n - tile_base) : (u64)TILE);
     if (count == TILE)
-        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, NMATCH, true, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
+        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, ST, true, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
     else
-        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, NMATCH, false, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
+        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, ST, false, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
 }
 
 // Tile shapes of the pass kernel; LIBSAIS_CUDA_SORT_VARIANT selects one for experiments.
@@ -376,17 +418,26 @@ struct RadixSort {
              + ceil_div(n, 3072) * kRadixSize * sizeof(u64);  // status of one pass (smallest tile of any variant)
     }
 
+    template <int THREADS, int IPT, int VALS, typename ST, typename Gen>
+    static void launch_pass_st(Ctx &c, const Gen &gen, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout, u64 n,
+                               int shift, u32 dmask, const u64 *base, u64 *status_raw, u32 *ticket, u32 *err)
+    {
+        typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
+        auto kern = sort_pass_kernel<KeyT, ValT, THREADS, IPT, VALS, ST, Gen>;
+        ST *status = reinterpret_cast<ST *>(status_raw);
+        c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        u64 nt = ceil_div(n, (u64)THREADS * IPT);
+        const double in_bytes = Gen::kActive ? 2.0 : (double)(sizeof(KeyT) + sizeof(ValT));   // generator: packed text + bwt byte
+        LSC_LAUNCH(c, Gen::kActive ? KC_SORT_PASS_GEN : KC_SORT_PASS, (double)n * (in_bytes + sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
+                   kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err, gen);
+    }
+
     template <int THREADS, int IPT, int VALS, typename Gen>
     static void launch_pass(Ctx &c, const Gen &gen, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout, u64 n,
                             int shift, u32 dmask, const u64 *base, u64 *status, u32 *ticket, u32 *err)
     {
-        typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
-        auto kern = sort_pass_kernel<KeyT, ValT, THREADS, IPT, VALS, 0, Gen>;
-        c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        u64 nt = ceil_div(n, (u64)THREADS * IPT);
-        const double in_bytes = Gen::kActive ? 2.0 : (double)(sizeof(KeyT) + sizeof(ValT));   // generator: packed text + bwt byte
-        LSC_LAUNCH(c, KC_SORT_PASS, (double)n * (in_bytes + sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
-                   kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err, gen);
+        if (n < (1ull << 30)) launch_pass_st<THREADS, IPT, VALS, u32, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err);
+        else                  launch_pass_st<THREADS, IPT, VALS, u64, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err);
     }
 
     template <typename Gen>
