@@ -234,7 +234,7 @@ IDX plcp_body(Ctx *c, const SYM *T, const IDX *SA, IDX *PLCP, IDX n)
     if (!c || !c->ok || (u64)n > kMaxN) return -2;
     Call call(*c);
     const size_t tb = (size_t)n * sizeof(SYM);
-    if (!c->reserve(tb + kPad + (size_t)n * (4 + 4 + 8 + 8) + 8192)) return -2;
+    if (!c->reserve(tb + kPad + (size_t)n * (4 + 4 + 8 + 8) + plcp_workspace_bytes((u64)n) + 8192)) return -2;
     const void *d_T = upload_text(*c, T, tb);
     u32 *d_SA = upload_indexes<IDX>(*c, SA, (u64)n);
     u32 *d_P = c->alloc_n<u32>((size_t)n);
@@ -473,7 +473,7 @@ int64_t libsais_cuda_plcp_dev(const void *ctx, const uint8_t *d_T, const uint32_
     if (!c || !c->ok || (u64)n > kMaxN) return -2;
     if (n == 0) return 0;
     Call call(*c);
-    if (!c->reserve((size_t)n + kPad + 4096)) return -2;
+    if (!c->reserve((size_t)n + kPad + plcp_workspace_bytes((u64)n) + 4096)) return -2;
     // own padded copy of the text: the compare kernel's 8-byte windows read past the end
     u8 *d_Tp = c->alloc_n<u8>((size_t)n + kPad);
     if (!d_Tp) return -2;

@@ -31,7 +31,7 @@ enum KernelClass {
     KC_RANK_SCAN,      // scan of the rank stage's tile aggregates
     KC_ROUND_KEYS,     // round>=1 key build (ISA gather)
     KC_RANK_UPDATE,    // round>=1 rank update + ISA scatter + compaction
-    KC_SMALL_SORT,     // round>=1 in-shared-memory sort of small active sets
+    KC_SCATTER,        // locality-partitioned scatter of (index, value) pairs (ISA, phi): partition pass + streaming scatter
     KC_BWT,            // BWT gather (+ primary, aux)
     KC_PHI,            // phi scatter
     KC_PLCP,           // PLCP compare
@@ -45,7 +45,7 @@ enum KernelClass {
 
 static const char *const kKernelClassName[KC_COUNT] = {
     "hist_sym", "pack", "make_keys", "sort_hist", "sort_scan", "sort_pass", "sort_pass_gen", "rank_init", "rank_scan",
-    "round_keys", "rank_update", "small_sort", "bwt", "phi", "plcp", "lcp",
+    "round_keys", "rank_update", "scatter", "bwt", "phi", "plcp", "lcp",
     "unbwt_prep", "unbwt_walk", "unbwt_rank", "convert"
 };
 

@@ -45,6 +45,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
 //   bwt:   U[n] from the per-slot rows produced by build_sa (SAOptions::bwt_rows) and the primary index
 int run_bwt_finish(Ctx &c, const u8 *d_T, const u8 *d_rows, u8 *d_U, u64 n, u64 primary);
 //   plcp:  PLCP[n] from T (sym_bytes 1 or 4), SA.  d_T must be readable up to 16 bytes past the end.
+size_t plcp_workspace_bytes(u64 n);
 int run_plcp(Ctx &c, const void *d_T, int sym_bytes, const u32 *d_SA, u32 *d_PLCP, u64 n);
 //   lcp:   LCP[i] = PLCP[SA[i]]
 int run_lcp(Ctx &c, const u32 *d_PLCP, const u32 *d_SA, u32 *d_LCP, u64 n);

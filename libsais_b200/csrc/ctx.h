@@ -36,6 +36,7 @@ struct Ctx {
 
     // launch accounting
     bool profiling = false;
+    int pass_class_override = -1;         // account onesweep launches to another kernel class (partitioned scatter)
     struct Pending { int kc; cudaEvent_t a, b; double bytes; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;

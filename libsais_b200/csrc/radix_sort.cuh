@@ -428,7 +428,8 @@ struct RadixSort {
         c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         u64 nt = ceil_div(n, (u64)THREADS * IPT);
         const double in_bytes = Gen::kActive ? 2.0 : (double)(sizeof(KeyT) + sizeof(ValT));   // generator: packed text + bwt byte
-        LSC_LAUNCH(c, Gen::kActive ? KC_SORT_PASS_GEN : KC_SORT_PASS, (double)n * (in_bytes + sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
+        const int kc = c.pass_class_override >= 0 ? c.pass_class_override : (Gen::kActive ? KC_SORT_PASS_GEN : KC_SORT_PASS);
+        LSC_LAUNCH(c, kc, (double)n * (in_bytes + sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
                    kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err, gen);
     }
 
@@ -472,10 +473,10 @@ struct RadixSort {
         {
             u64 want = ceil_div(n, (u64)HIST_THREADS * 8);
             u32 grid = (u32)(want < (u64)c.sm_count * 4 ? (want ? want : 1) : (u64)c.sm_count * 4);
-            LSC_LAUNCH(c, KC_SORT_HIST, (double)n * (Gen::kActive ? 2.0 : (double)sizeof(KeyT)), (sort_hist_kernel<KeyT, HIST_THREADS, Gen>),
+            LSC_LAUNCH(c, c.pass_class_override >= 0 ? c.pass_class_override : KC_SORT_HIST, (double)n * (Gen::kActive ? 2.0 : (double)sizeof(KeyT)), (sort_hist_kernel<KeyT, HIST_THREADS, Gen>),
                        grid, HIST_THREADS, 0, ka, n, plan, hist, gen);
         }
-        LSC_LAUNCH(c, KC_SORT_SCAN, 0.0, sort_scan_kernel, plan.passes, kRadixSize, 0, hist, base);
+        LSC_LAUNCH(c, c.pass_class_override >= 0 ? c.pass_class_override : KC_SORT_SCAN, 0.0, sort_scan_kernel, plan.passes, kRadixSize, 0, hist, base);
 
         KeyT *kin = ka, *kout = kb; ValT *vin = va, *vout = vb;
         int where = 0;

@@ -19,6 +19,7 @@
 // key, exactly as an implicit smallest sentinel would order them.
 #include "core.h"
 #include "radix_sort.cuh"
+#include "scatter.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -170,6 +171,7 @@ struct RankArgs {
     u64 N; u64 tail_start; int key_shift;
     u32 *SA;                 // nullable: SA[slot] = pos
     u32 *ISA; int isa_all;   // isa_all: write every element's rank, else only the active ones
+    u32 *pair_idx, *pair_val; // non-null: emit (position, rank) pairs in element order instead of scattering into ISA
     u8 *rows; const u8 *text;            // BWT mode: rows[slot] = byte preceding the suffix
     u64 aux_mask; int aux_shift; u32 *aux_I;
     u64 *primary;
@@ -396,7 +398,8 @@ rank_apply_kernel(const RankArgs a)
         const u32 rank = hle ? hs : c_head;
         if (j < N) {
             const bool act = (am[i] >> lane) & 1;
-            if (a.isa_all || act) a.ISA[p[i]] = rank;
+            if (a.pair_idx) { a.pair_idx[j] = p[i]; a.pair_val[j] = rank; }
+            else if (a.isa_all || act) a.ISA[p[i]] = rank;
             if (act) {
                 const u32 o = c_act + __popc(am[i] & lt);
                 a.a_pos[o] = p[i];
@@ -408,21 +411,6 @@ rank_apply_kernel(const RankArgs a)
         c_act += __popc(am[i]);
         c_grp += __popc(gm[i]);
     }
-}
-
-// After round 0, when many suffixes stay active the full ISA is needed: ranks of the singletons.
-__global__ void __launch_bounds__(256)
-isa_fill_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ pos, u64 N, u64 tail_start, int key_shift,
-                u32 *__restrict__ ISA)
-{
-    u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (j >= N) return;
-    u64 k = keys[j] >> key_shift;
-    u32 p = pos[j];
-    bool tail = (u64)p >= tail_start;
-    bool head = (j == 0) || ((keys[j - 1] >> key_shift) != k) || tail || (u64)pos[j - (j ? 1 : 0)] >= tail_start;
-    bool nexthead = (j + 1 == N) || ((keys[j + 1] >> key_shift) != k) || tail || (u64)pos[j + (j + 1 < N ? 1 : 0)] >= tail_start;
-    if (head && nexthead) ISA[p] = (u32)j;
 }
 
 // Lazy ISA: rank of a round-0 singleton q, recomputed from the sorted round-0 keys.
@@ -605,9 +593,9 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     ra.a_pos = a_pos; ra.a_slot = slot_cur; ra.a_grp = a_grp;
     ra.masks = rmasks; ra.wagg = rwagg; ra.tagg = rtagg; ra.nchunks = ceil_div(n, 32);
     ra.ntiles = rank_tiles; ra.out_counts = c.d_scalars + S_NACT;
+    ra.pair_idx = nullptr; ra.pair_val = nullptr;
     LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
     LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, 1, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
-    LSC_LAUNCH(c, KC_RANK_INIT, 0.0, rank_apply_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
     if (!read_round_scalars(c)) return -2;
     u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
     rs.n_groups = G;
@@ -625,9 +613,15 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
                 lazy = false; rk0 = ks; rk1 = ko; rv0 = vs; rv1 = vo; c.last_error = cudaSuccess;
             }
         }
-        if (!lazy)
-            LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + 4), isa_fill_kernel, (u32)ceil_div(n, 256), 256, 0,
-                       ks, vs, n, tail_start, key_shift, ISA);
+        if (lazy) {
+            ra.isa_all = 0;
+            LSC_LAUNCH(c, KC_RANK_INIT, (double)N * 16, rank_apply_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+        } else {
+            // every rank is needed: (position, rank) pairs in slot order, then a locality-partitioned scatter
+            ra.isa_all = 1; ra.pair_idx = (u32 *)ko; ra.pair_val = (u32 *)ko + n;
+            LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (4 + 8) + (double)N * 12, rank_apply_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+            if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)ks, (u32 *)ks + n, n, n, ISA, sort_temp, err) != 0) return -2;
+        }
     }
     LazyArgs la; la.words = words; la.b = b; la.K = K; la.s0_keys = ks; la.s0_pos = vs; la.key_shift = key_shift;
     la.tail_start = tail_start; la.n = n;
@@ -649,9 +643,15 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         const u64 tiles = ceil_div(N, kRankTile);
         ra.keys = where ? rk1 : rk0; ra.pos = where ? rv1 : rv0; ra.slot_in = slot_cur; ra.N = N; ra.tail_start = 0; ra.key_shift = 0;
         ra.isa_all = 1; ra.a_slot = slot_nxt; ra.ntiles = tiles; ra.nchunks = ceil_div(N, 32);
+        u64 *other_k = where ? rk0 : rk1;                     // the ping-pong half not holding the sorted result
+        ra.pair_idx = (u32 *)other_k; ra.pair_val = (u32 *)other_k + N;
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 4), rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
         LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, 1, 1024, 0, rtagg, tiles, c.d_scalars + S_NACT);
-        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (4 + 4 + 4 + 12), rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (4 + 4 + 8 + 12), rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        {   // new ranks -> ISA; the sorted (key, pos) buffer is dead now and serves as partition scratch
+            u64 *sorted_k = where ? rk1 : rk0;
+            if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)sorted_k, (u32 *)sorted_k + N, N, n, ISA, sort_temp, err) != 0) return -2;
+        }
         if (!read_round_scalars(c)) return -2;
         N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
         r.n_groups = G;

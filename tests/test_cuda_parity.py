@@ -100,6 +100,41 @@ def test_repetitive_dna_vs_oracle(cu):
     _full_compare(cu, _libs.oracle(), T)
 
 
+def test_repetitive_dna_19m_partitioned_scatter_vs_oracle(cu):
+    """BASELINE config 3 at 1/100 scale (19 M symbols): large enough that the ISA updates and the
+    phi array go through the locality-partitioned scatter and most suffixes stay active for ~10 rounds."""
+    T = gen.repetitive_dna(190000, 100)
+    o = _libs.oracle()
+    a, b = cu.sa(T), o.sa(T)
+    assert a[0] == b[0] == 0 and (a[1] == b[1]).all()
+    SA = b[1]
+    a, b = cu.bwt(T), o.bwt(T)
+    assert a[0] == b[0] and (a[1] == b[1]).all()
+    p1, p2 = cu.plcp(T, SA), o.plcp(T, SA)
+    assert p1[0] == 0 and (p1[1] == p2[1]).all()
+    l1 = cu.lcp(p2[1], SA)
+    assert l1[0] == 0 and (l1[1] == p2[1][SA]).all()
+    u = cu.unbwt(a[1], a[0])
+    assert u[0] == 0 and (u[1] == T).all()
+
+
+def test_forced_isa_modes_agree(cu):
+    """Lazy ISA (binary-search fallback) and full ISA (partitioned scatter) are two routes to the same SA."""
+    import os
+    o = _libs.oracle()
+    T = np.concatenate([gen.dna(5, 300000), gen.dna(5, 300000), gen.rand_bytes(6, 200000)])
+    want = o.sa(T)[1]
+    try:
+        for mode in ("0", "1"):
+            os.environ["LIBSAIS_CUDA_LAZY_ISA"] = mode
+            rc, SA = cu.sa(T)
+            assert rc == 0 and (SA == want).all(), mode
+            rcb, U = cu.bwt(T)
+            assert (rcb, U.tobytes()) == (o.bwt(T)[0], o.bwt(T)[1].tobytes()), mode
+    finally:
+        os.environ.pop("LIBSAIS_CUDA_LAZY_ISA", None)
+
+
 def test_adversarial_periodic_inputs_vs_oracle(cu):
     o = _libs.oracle()
     for T in (np.zeros(1 << 17, dtype=np.uint8), np.resize(np.frombuffer(b"ab", dtype=np.uint8), (1 << 17) + 1),
@@ -160,6 +195,51 @@ def test_device_pointer_entry_points_roundtrip(cu):
     assert (dBack.cpu().numpy() == T).all()
     st = ctx.stats()
     assert st["total_launches"] > 0
+    ctx.close()
+
+
+def _verify_sa_on_gpu(dT, dSA, n, chunk=1 << 27):
+    """Linear-time SA check with torch ops on the GPU: permutation + Burkhardt-Kaerkkaeinen neighbour order."""
+    import torch
+    seen = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for lo in range(0, n, chunk):
+        seen[dSA[lo:lo + chunk].long()] = 1
+    assert bool(seen.all()), "SA is not a permutation"
+    del seen
+    ISA = torch.empty(n, dtype=torch.int32, device="cuda")
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        ISA[dSA[lo:hi].long()] = torch.arange(lo, hi, dtype=torch.int32, device="cuda")
+    for lo in range(1, n, chunk):
+        hi = min(n, lo + chunk)
+        a = dSA[lo - 1:hi - 1].long(); b = dSA[lo:hi].long()
+        ta, tb = dT[a], dT[b]
+        ra = torch.where(a + 1 < n, ISA[torch.clamp(a + 1, max=n - 1)], torch.full_like(ISA[:1], -1))
+        rb = torch.where(b + 1 < n, ISA[torch.clamp(b + 1, max=n - 1)], torch.full_like(ISA[:1], -1))
+        assert bool(((ta < tb) | ((ta == tb) & (ra < rb))).all()), "suffix order violated"
+    return ISA
+
+
+def test_n_above_2pow30_device_api_properties(cu):
+    """n = 2^30 + 12345 iid ACGT through the device-pointer API: exercises the 64-bit tile status
+    words of the onesweep pass (n >= 2^30); checked by the linear-time SA verifier on the GPU and
+    by unbwt(bwt(T)) == T."""
+    import torch
+    import libsais_b200
+    n = (1 << 30) + 12345
+    T = gen.dna(5, n)
+    ctx = libsais_b200.Context(0)
+    dT = torch.from_numpy(T).cuda()
+    dSA = torch.empty(n, dtype=torch.int32, device="cuda")
+    assert ctx.sa_dev(dT.data_ptr(), dSA.data_ptr(), n) == 0
+    ISA = _verify_sa_on_gpu(dT, dSA, n)
+    dU = torch.empty(n, dtype=torch.uint8, device="cuda")
+    primary = ctx.bwt_dev(dT.data_ptr(), dU.data_ptr(), n)
+    assert primary == int(ISA[0]) + 1
+    del ISA, dSA
+    dB = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert ctx.unbwt_dev(dU.data_ptr(), dB.data_ptr(), n, primary) == 0
+    assert torch.equal(dB, dT)
     ctx.close()
 
 
