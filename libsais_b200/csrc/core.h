@@ -13,7 +13,8 @@ enum ScalarSlot {
     S_MAXSYM  = 259,   // max symbol of an integer text
     S_PRIMARY = 260,   // slot of suffix 0 (+1)
     S_TICKET  = 264,   // [264, 272): tickets of the rank kernels (u32 views)
-    S_MISC    = 272
+    S_MISC    = 272,   // [272, 304): LUT staging; [312, 320): debug counters
+    S_SGRAM   = 512    // [512, 768): s-gram histogram of the text
 };
 
 struct SAOptions {

@@ -457,8 +457,9 @@ struct RadixSort {
     // buffer.  Returns 0 when the result is in (ka, va), 1 when in (kb, vb), -1 on error.
     template <typename Gen>
     static int sort_from(Ctx &c, const Gen &gen, KeyT *ka, ValT *va, KeyT *kb, ValT *vb, u64 n, int lo_bit, int hi_bit,
-                         void *temp, u32 *err, int *passes_out = nullptr)
+                         void *temp, u32 *err, int *passes_out = nullptr, bool hist_ready = false)
     {
+        // hist_ready: the caller already wrote the digit histograms (u64[passes][256]) at the start of `temp`
         SortPlan plan = make_sort_plan(lo_bit, hi_bit);
         if (passes_out) *passes_out = plan.passes;
         if (n == 0 || plan.passes == 0) return Gen::kActive ? -1 : 0;
@@ -469,8 +470,9 @@ struct RadixSort {
         u64 *status = (u64 *)t;
         const u64 nt = tiles(n);
 
-        c.check(cudaMemsetAsync(hist, 0, 2 * kMaxPasses * kRadixSize * sizeof(u64) + 256, c.stream));
-        {
+        if (hist_ready) c.check(cudaMemsetAsync(tickets, 0, 256, c.stream));
+        else c.check(cudaMemsetAsync(hist, 0, 2 * kMaxPasses * kRadixSize * sizeof(u64) + 256, c.stream));
+        if (!hist_ready) {
             u64 want = ceil_div(n, (u64)HIST_THREADS * 8);
             u32 grid = (u32)(want < (u64)c.sm_count * 4 ? (want ? want : 1) : (u64)c.sm_count * 4);
             LSC_LAUNCH(c, c.pass_class_override >= 0 ? c.pass_class_override : KC_SORT_HIST, (double)n * (Gen::kActive ? 2.0 : (double)sizeof(KeyT)), (sort_hist_kernel<KeyT, HIST_THREADS, Gen>),

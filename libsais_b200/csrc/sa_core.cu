@@ -161,10 +161,11 @@ make_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int K, int key_shi
 //   rank_apply  streaming over the tiles that contain work: rank -> ISA, compaction of the actives
 // ---------------------------------------------------------------------------------------------
 static const int kRankThreads = 256;
-static const int kRankIPT = 8;
+static const int kRankIPT = 4;
 static const int kRankTile = kRankThreads * kRankIPT;
 static const int kRankWarps = kRankThreads / 32;
 static const u32 kIsaInvalid = 0xFFFFFFFFu;
+__device__ __forceinline__ u64 ceil_div_dev(u64 a, u64 b) { return (a + b - 1) / b; }
 
 struct RankArgs {
     const u64 *keys; const u32 *pos; const u32 *slot_in;
@@ -452,6 +453,76 @@ round_keys_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Round-0 digit histograms without touching the keys.  When a digit is a whole number of symbols
+// (b divides 8) digit j of suffix p is the s-gram (s = 8/b symbols) at text position
+// p + s*(P-1-j): every pass's histogram is the s-gram histogram H of the whole text, minus the
+// s-grams before that offset, plus the zero padding past the end.  For bytes (b = 8) H is the
+// byte histogram that was needed anyway (freq); for smaller alphabets one pass over the packed text.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 sgram_at(const u64 *__restrict__ words, u64 q, int b)
+{
+    u64 bit = q * (u64)b;
+    u64 w = bit >> 6; int off = (int)(bit & 63);
+    u64 hi = words[w], lo = words[w + 1];
+    u64 x = off ? ((hi << off) | (lo >> (64 - off))) : hi;
+    return (u32)(x >> 56);
+}
+
+__global__ void __launch_bounds__(256)
+sgram_hist_kernel(const u64 *__restrict__ words, u64 n, int b, u64 *__restrict__ H)
+{
+    __shared__ u32 sh[8][256];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 8 * 256; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const int per = 64 / b;                                   // positions whose s-gram starts in one word
+    const u64 nw = ceil_div_dev(n * (u64)b, 64);
+    for (u64 w = (u64)blockIdx.x * 256 + tid; w < nw; w += (u64)gridDim.x * 256) {
+        u64 hi = words[w], lo = words[w + 1];
+        u64 q0 = w * (u64)per;
+        for (int i = 0; i < per; ++i) {
+            if (q0 + i >= n) break;
+            int off = i * b;
+            u64 x = off ? ((hi << off) | (lo >> (64 - off))) : hi;
+            atomicAdd(&sh[warp][(u32)(x >> 56)], 1u);
+        }
+    }
+    __syncthreads();
+    u32 t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][tid];
+    if (t) atomicAdd((unsigned long long *)&H[tid], (unsigned long long)t);
+}
+
+// b = 8: H[code] = freq[symbol]
+__global__ void sgram_from_freq_kernel(const u64 *__restrict__ freq, const u8 *__restrict__ lut, u64 *__restrict__ H)
+{
+    int s = threadIdx.x;
+    u64 f = freq[s];
+    if (f) H[lut[s]] = f;          // codes of present symbols are distinct
+}
+
+// grid = passes: hist[j] = H - (s-grams at positions < off_j) + off_j zero-padded windows past the end
+__global__ void __launch_bounds__(256)
+digit_hist_from_sgram_kernel(const u64 *__restrict__ H, const u64 *__restrict__ words, u64 n, int b, int passes,
+                             u64 *__restrict__ hist)
+{
+    __shared__ unsigned long long sh[256];
+    const int j = blockIdx.x, t = threadIdx.x;
+    const int s = 8 / b;
+    const u64 off = (u64)s * (u64)(passes - 1 - j);
+    sh[t] = H[t];
+    __syncthreads();
+    // windows at positions [0, off) leave; `off` windows that start past the end (all padding, value 0) enter
+    for (u64 q = t; q < off; q += 256) {
+        if (q < n) atomicAdd(&sh[sgram_at(words, q, b)], (unsigned long long)-1ll);
+        atomicAdd(&sh[0], 1ull);
+    }
+    __syncthreads();
+    hist[j * 256 + t] = sh[t];
+}
+
+// ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
 size_t sa_workspace_bytes(u64 n, int sym_bytes)
@@ -572,7 +643,26 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     int where;
     if (fuse_keys) {
         KmerGen gen; gen.words = words; gen.text = bwt_mode ? (const u8 *)d_T : nullptr; gen.n = n; gen.b = b; gen.K = K; gen.key_shift = key_shift;
-        where = RadixSort<u64, u32>::sort_from<KmerGen>(c, gen, keyA, valA, keyB, valB, n, key_shift, key_shift + K, sort_temp, err, &rs.passes);
+        // digit histograms straight from the s-gram histogram of the text when digits are symbol aligned
+        bool hist_ready = false;
+        const int passes0 = (K + kRadixBits - 1) / kRadixBits;
+        bool sgram = (8 % b) == 0 && (K % 8) == 0 && n > 4096;
+        { const char *env = getenv("LIBSAIS_CUDA_SGRAM_HIST"); if (env && *env) sgram = sgram && atoi(env) != 0; }
+        if (sgram) {
+            u64 *H = c.d_scalars + S_SGRAM;
+            u64 *hist = (u64 *)sort_temp;
+            c.check(cudaMemsetAsync(H, 0, 256 * sizeof(u64), st));
+            if (b == 8 && sym_bytes == 1) {
+                LSC_LAUNCH(c, KC_SORT_HIST, 0.0, sgram_from_freq_kernel, 1, 256, 0, c.d_scalars + S_FREQ, d_lut, H);
+            } else {
+                u64 nw = ceil_div(n * (u64)b, 64);
+                u32 grid = (u32)(ceil_div(nw, 256 * 8) < (u64)c.sm_count * 8 ? ceil_div(nw, 256 * 8) : (u64)c.sm_count * 8);
+                LSC_LAUNCH(c, KC_SORT_HIST, (double)nw * 8, sgram_hist_kernel, grid ? grid : 1, 256, 0, words, n, b, H);
+            }
+            LSC_LAUNCH(c, KC_SORT_HIST, 0.0, digit_hist_from_sgram_kernel, passes0, 256, 0, H, words, n, b, passes0, hist);
+            hist_ready = true;
+        }
+        where = RadixSort<u64, u32>::sort_from<KmerGen>(c, gen, keyA, valA, keyB, valB, n, key_shift, key_shift + K, sort_temp, err, &rs.passes, hist_ready);
     } else {
         LSC_LAUNCH(c, KC_MAKE_KEYS, (double)nwords * 8 + (double)n * (12 + (bwt_mode ? 1 : 0)), make_keys_kernel,
                    (u32)ceil_div(n, 256), 256, 0, words, n, b, K, key_shift, bwt_mode ? (const u8 *)d_T : (const u8 *)nullptr, keyA, valA);
