@@ -165,6 +165,59 @@ IDX sa_int_body(Ctx *c, SYM *T, IDX *SA, IDX n, IDX k, IDX fs)
     return 0;
 }
 
+// Generalized SA (reference libsais_gsa, src/libsais.c:7033-7048): SA of the separator-ranked integer text.
+template <typename IDX>
+IDX gsa_body(Ctx *c, const uint8_t *T, IDX *SA, IDX n, IDX fs, IDX *freq)
+{
+    if (T == nullptr || SA == nullptr || n < 0 || (n > 0 && T[n - 1] != 0) || fs < 0) return -1;
+    if (n <= 1) { host_freq(T, n, freq); if (n == 1) SA[0] = 0; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN - 512) return -2;
+    Call call(*c);
+    if (!c->reserve((size_t)n + kPad + gsa_workspace_bytes((u64)n) + sa_workspace_bytes((u64)n, 4) + 8192)) return -2;
+    const u8 *d_T = (const u8 *)upload_text(*c, T, (size_t)n);
+    if (!d_T) return -2;
+    call.start_timer();
+    if (freq) run_byte_histogram(*c, d_T, (u64)n);
+    if (freq) c->check(cudaMemcpyAsync(c->h_scalars + S_FREQ, c->d_scalars + S_FREQ, 256 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    const u32 *d_Tint = build_gsa_text(*c, d_T, (u64)n);
+    if (!d_Tint) return -2;
+    // empty members (T[0] == 0 or "00") are rejected like the reference does (src/libsais.c:6886-6889)
+    c->check(cudaMemcpyAsync(c->h_scalars + S_GSA_INVALID, c->d_scalars + S_GSA_INVALID, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    if (!c->sync()) return -2;
+    if (c->h_scalars[S_GSA_INVALID] != 0) return -1;
+    SAResult res; SAOptions opt;
+    if (build_sa(*c, d_Tint, 4, (u64)n, opt, &res) != 0) return -2;
+    call.stop_timer();
+    download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
+    if (!call.finish()) return -2;
+    store_freq(*c, freq);
+    return 0;
+}
+
+// PLCP of a generalized SA (reference libsais_plcp_gsa, :8381-8397): matches stop at the separators.
+template <typename IDX>
+IDX plcp_gsa_body(Ctx *c, const uint8_t *T, const IDX *SA, IDX *PLCP, IDX n)
+{
+    if (T == nullptr || SA == nullptr || PLCP == nullptr || n < 0 || (n > 0 && T[n - 1] != 0)) return -1;
+    if (n <= 1) { if (n == 1) PLCP[0] = 0; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN - 512) return -2;
+    Call call(*c);
+    if (!c->reserve((size_t)n + kPad + gsa_workspace_bytes((u64)n) + (size_t)n * (4 + 4 + 8 + 8) + plcp_workspace_bytes((u64)n) + 8192)) return -2;
+    const u8 *d_T = (const u8 *)upload_text(*c, T, (size_t)n);
+    u32 *d_SA = upload_indexes<IDX>(*c, SA, (u64)n);
+    u32 *d_P = c->alloc_n<u32>((size_t)n);
+    void *wide = sizeof(IDX) == 8 ? c->alloc((size_t)n * 8) : nullptr;
+    if (!d_T || !d_SA || !d_P || (sizeof(IDX) == 8 && !wide)) return -2;
+    call.start_timer();
+    const u32 *d_Tint = build_gsa_text(*c, d_T, (u64)n);
+    if (!d_Tint) return -2;
+    if (run_plcp(*c, d_Tint, 4, d_SA, d_P, (u64)n) != 0) return -2;
+    call.stop_timer();
+    download_indexes<IDX>(*c, d_P, PLCP, (u64)n, wide);
+    if (!call.finish()) return -2;
+    return 0;
+}
+
 // BWT with optional aux sampling (r == 0: none).  Returns primary index (r == 0) or 0.
 template <typename IDX>
 IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *freq, IDX r, IDX *I, bool aux)
@@ -294,12 +347,17 @@ int32_t libsais_int(int32_t *T, int32_t *SA, int32_t n, int32_t k, int32_t fs)
 int32_t libsais_int_omp(int32_t *T, int32_t *SA, int32_t n, int32_t k, int32_t fs, int32_t threads)
 { if (threads < 0) return -1; return sa_int_body<int32_t, int32_t>(default_ctx(), T, SA, n, k, fs); }
 
-// generalized suffix arrays: exported so existing programs link; not supported yet
-int32_t libsais_gsa(const uint8_t *, int32_t *, int32_t, int32_t, int32_t *) { return -1; }
-int32_t libsais_gsa_ctx(const void *, const uint8_t *, int32_t *, int32_t, int32_t, int32_t *) { return -1; }
-int32_t libsais_gsa_omp(const uint8_t *, int32_t *, int32_t, int32_t, int32_t *, int32_t) { return -1; }
-int32_t libsais_plcp_gsa(const uint8_t *, const int32_t *, int32_t *, int32_t) { return -1; }
-int32_t libsais_plcp_gsa_omp(const uint8_t *, const int32_t *, int32_t *, int32_t, int32_t) { return -1; }
+// generalized suffix arrays
+int32_t libsais_gsa(const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq)
+{ return gsa_body<int32_t>(default_ctx(), T, SA, n, fs, freq); }
+int32_t libsais_gsa_ctx(const void *ctx, const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq)
+{ if (ctx == nullptr) return -1; return gsa_body<int32_t>(as_ctx(ctx), T, SA, n, fs, freq); }
+int32_t libsais_gsa_omp(const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq, int32_t threads)
+{ if (threads < 0) return -1; return gsa_body<int32_t>(default_ctx(), T, SA, n, fs, freq); }
+int32_t libsais_plcp_gsa(const uint8_t *T, const int32_t *SA, int32_t *PLCP, int32_t n)
+{ return plcp_gsa_body<int32_t>(default_ctx(), T, SA, PLCP, n); }
+int32_t libsais_plcp_gsa_omp(const uint8_t *T, const int32_t *SA, int32_t *PLCP, int32_t n, int32_t threads)
+{ if (threads < 0) return -1; return plcp_gsa_body<int32_t>(default_ctx(), T, SA, PLCP, n); }
 
 int32_t libsais_bwt(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq)
 { return bwt_body<int32_t>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }
@@ -350,10 +408,14 @@ int64_t libsais64_long(int64_t *T, int64_t *SA, int64_t n, int64_t k, int64_t fs
 int64_t libsais64_long_omp(int64_t *T, int64_t *SA, int64_t n, int64_t k, int64_t fs, int64_t threads)
 { if (threads < 0) return -1; return sa_int_body<int64_t, int64_t>(default_ctx(), T, SA, n, k, fs); }
 
-int64_t libsais64_gsa(const uint8_t *, int64_t *, int64_t, int64_t, int64_t *) { return -1; }
-int64_t libsais64_gsa_omp(const uint8_t *, int64_t *, int64_t, int64_t, int64_t *, int64_t) { return -1; }
-int64_t libsais64_plcp_gsa(const uint8_t *, const int64_t *, int64_t *, int64_t) { return -1; }
-int64_t libsais64_plcp_gsa_omp(const uint8_t *, const int64_t *, int64_t *, int64_t, int64_t) { return -1; }
+int64_t libsais64_gsa(const uint8_t *T, int64_t *SA, int64_t n, int64_t fs, int64_t *freq)
+{ return gsa_body<int64_t>(default_ctx(), T, SA, n, fs, freq); }
+int64_t libsais64_gsa_omp(const uint8_t *T, int64_t *SA, int64_t n, int64_t fs, int64_t *freq, int64_t threads)
+{ if (threads < 0) return -1; return gsa_body<int64_t>(default_ctx(), T, SA, n, fs, freq); }
+int64_t libsais64_plcp_gsa(const uint8_t *T, const int64_t *SA, int64_t *PLCP, int64_t n)
+{ return plcp_gsa_body<int64_t>(default_ctx(), T, SA, PLCP, n); }
+int64_t libsais64_plcp_gsa_omp(const uint8_t *T, const int64_t *SA, int64_t *PLCP, int64_t n, int64_t threads)
+{ if (threads < 0) return -1; return plcp_gsa_body<int64_t>(default_ctx(), T, SA, PLCP, n); }
 
 int64_t libsais64_bwt(const uint8_t *T, uint8_t *U, int64_t *A, int64_t n, int64_t fs, int64_t *freq)
 { return bwt_body<int64_t>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }

@@ -14,6 +14,8 @@ enum ScalarSlot {
     S_PRIMARY = 260,   // slot of suffix 0 (+1)
     S_TICKET  = 264,   // [264, 272): tickets of the rank kernels (u32 views)
     S_MISC    = 272,   // [272, 304): LUT staging; [312, 320): debug counters
+    S_GSA_TOTAL = 320, // number of separators of a GSA text
+    S_GSA_INVALID = 321, // set when the collection has an empty member (reference returns -1)
     S_SGRAM   = 512    // [512, 768): s-gram histogram of the text
 };
 
@@ -53,6 +55,10 @@ int run_lcp(Ctx &c, const u32 *d_PLCP, const u32 *d_SA, u32 *d_LCP, u64 n);
 //   unbwt: text U[n] from BWT B[n] and the primary index
 size_t unbwt_workspace_bytes(u64 n);
 int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary);
+
+// generalized suffix arrays: integer text with one distinct symbol per separator (gsa.cu)
+size_t gsa_workspace_bytes(u64 n);
+u32 *build_gsa_text(Ctx &c, const u8 *d_T, u64 n);
 
 // conversions used by the 64-bit API
 void run_widen(Ctx &c, const u32 *src, i64 *dst, u64 n);

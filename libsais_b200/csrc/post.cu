@@ -16,14 +16,29 @@ namespace lsc {
 __global__ void __launch_bounds__(256)
 bwt_finish_kernel(const u8 *__restrict__ T, const u8 *__restrict__ rows, u8 *__restrict__ U, u64 n, u64 p0)
 {
-    u64 o = (u64)blockIdx.x * 256 + threadIdx.x;       // output index
-    if (o >= n) return;
-    U[o] = o == 0 ? T[n - 1] : rows[o <= p0 ? o - 1 : o];
+    // 16 output bytes per thread: U[o] = rows[o - 1] for 1 <= o <= p0, rows[o] for o > p0, U[0] = T[n-1]
+    const u64 o0 = ((u64)blockIdx.x * 256 + threadIdx.x) * 16;
+    if (o0 >= n) return;
+    const bool aligned = (((uintptr_t)U | (uintptr_t)rows) & 15) == 0;
+    if (aligned && o0 + 16 <= n && o0 > p0) {                       // whole group after the dropped row: straight copy
+        *reinterpret_cast<uint4 *>(U + o0) = *reinterpret_cast<const uint4 *>(rows + o0);
+        return;
+    }
+    if (aligned && o0 + 16 <= n && o0 + 15 <= p0 && o0 >= 16) {     // whole group before it: shifted by one byte
+        const uint4 a = *reinterpret_cast<const uint4 *>(rows + o0 - 16), c = *reinterpret_cast<const uint4 *>(rows + o0);
+        uint4 r;
+        r.x = __funnelshift_l(a.w, c.x, 8); r.y = __funnelshift_l(c.x, c.y, 8);
+        r.z = __funnelshift_l(c.y, c.z, 8); r.w = __funnelshift_l(c.z, c.w, 8);
+        *reinterpret_cast<uint4 *>(U + o0) = r;
+        return;
+    }
+    for (u64 o = o0; o < o0 + 16 && o < n; ++o)
+        U[o] = o == 0 ? T[n - 1] : rows[o <= p0 ? o - 1 : o];
 }
 
 int run_bwt_finish(Ctx &c, const u8 *d_T, const u8 *d_rows, u8 *d_U, u64 n, u64 primary)
 {
-    LSC_LAUNCH(c, KC_BWT, (double)n * 2, bwt_finish_kernel, (u32)ceil_div(n, 256), 256, 0, d_T, d_rows, d_U, n, primary - 1);
+    LSC_LAUNCH(c, KC_BWT, (double)n * 2, bwt_finish_kernel, (u32)ceil_div(ceil_div(n, 16), 256), 256, 0, d_T, d_rows, d_U, n, primary - 1);
     return c.failed() ? -2 : 0;
 }
 

@@ -304,6 +304,53 @@ int64_t oracle_libsais64_long(int64_t *T, int64_t *SA, int64_t n, int64_t k, int
     return libsais64_sa(T, 8, SA, n, kk);
 }
 
+/* Generalized suffix array (reference libsais_gsa, src/libsais.c:7033-7048; GSA induction :3022-3053,
+ * :5472-5492): every 0 byte is a distinct terminator ordered by position.  Restated by its definition:
+ * the plain SA of the text in which the i-th separator is replaced by symbol i and byte c by m + c. */
+#define DEFINE_GSA(PFX, IDX)                                                                     \
+static i64 *PFX##_gsa_text(const uint8_t *T, IDX n, i64 *k_out)                                  \
+{                                                                                                \
+    i64 i, m = 0, z = 0, *X = (i64 *)malloc((size_t)(n > 0 ? n : 1) * sizeof(i64));              \
+    if (!X) return NULL;                                                                         \
+    for (i = 0; i < (i64)n; ++i) m += T[i] == 0;                                                 \
+    for (i = 0; i < (i64)n; ++i) X[i] = T[i] == 0 ? z++ : m + T[i];                              \
+    *k_out = m + 256;                                                                            \
+    return X;                                                                                    \
+}                                                                                                \
+IDX oracle_##PFX##_gsa(const uint8_t *T, IDX *SA, IDX n, IDX fs, IDX *freq)                      \
+{                                                                                                \
+    i64 k, *X; IDX rc;                                                                           \
+    if (!T || !SA || n < 0 || (n > 0 && T[n - 1] != 0) || fs < 0) return -1;                     \
+    PFX##_count(T, n, freq);                                                                     \
+    if (n <= 1) { if (n == 1) SA[0] = 0; return 0; }                                             \
+    /* the reference rejects empty members (libsais_main_8u :6886-6889, bucket test on symbol 0): \
+       verified exhaustively against the compiled reference for n <= 7: T[0] != 0, no "00" */      \
+    if (T[0] == 0) return -1;                                                                    \
+    { IDX q; for (q = 1; q < n; ++q) if (T[q] == 0 && T[q - 1] == 0) return -1; }                \
+    X = PFX##_gsa_text(T, n, &k); if (!X) return -2;                                             \
+    rc = PFX##_sa(X, 8, SA, n, k);                                                               \
+    free(X);                                                                                     \
+    return rc;                                                                                   \
+}                                                                                                \
+/* PLCP of a GSA (reference compute_plcp_gsa :8215-8238): matches stop at (exclude) separators */ \
+IDX oracle_##PFX##_plcp_gsa(const uint8_t *T, const IDX *SA, IDX *PLCP, IDX n)                   \
+{                                                                                                \
+    IDX i, l, prev;                                                                              \
+    if (!T || !SA || !PLCP || n < 0 || (n > 0 && T[n - 1] != 0)) return -1;                      \
+    if (n <= 1) { if (n == 1) PLCP[0] = 0; return 0; }                                           \
+    for (i = 0, prev = n; i < n; ++i) { PLCP[SA[i]] = prev; prev = SA[i]; }                      \
+    for (i = 0, l = 0; i < n; ++i) {                                                             \
+        IDX k = PLCP[i];                                                                         \
+        if (k == n) l = 0;                                                                       \
+        else while (T[i + l] > 0 && T[i + l] == T[k + l]) ++l;                                   \
+        PLCP[i] = l; if (l > 0) --l;                                                             \
+    }                                                                                            \
+    return 0;                                                                                    \
+}
+
+DEFINE_GSA(libsais, int32_t)
+DEFINE_GSA(libsais64, int64_t)
+
 /* Brute-force definitional checker (second, independent oracle for tiny n): returns the
  * number of adjacent pairs of SA that are out of order or 0 if SA is the sorted suffix order. */
 int64_t oracle_check_sa_bruteforce(const uint8_t *T, const int64_t *SA, int64_t n)

@@ -51,6 +51,24 @@ class Impl:
         rc = self._f(name, bits)(ptr(T), ptr(SA), ct(n), ct(fs), ptr(freq))
         return (rc, SA[:n], freq) if want_freq else (rc, SA[:n])
 
+    def gsa(self, T, bits=32, want_freq=False):
+        dt, ct = self._it(bits)
+        n = len(T)
+        SA = np.full(max(n, 1), -7, dtype=dt)
+        freq = np.full(256, -1, dtype=dt) if want_freq else None
+        name = "libsais_gsa" if bits == 32 else "libsais64_gsa"
+        rc = self._f(name, bits)(ptr(T), ptr(SA), ct(n), ct(0), ptr(freq))
+        return (rc, SA[:n], freq) if want_freq else (rc, SA[:n])
+
+    def plcp_gsa(self, T, SA, bits=32):
+        dt, ct = self._it(bits)
+        n = len(T)
+        SA = np.ascontiguousarray(SA, dtype=dt)
+        P = np.full(max(n, 1), -7, dtype=dt)
+        name = "libsais_plcp_gsa" if bits == 32 else "libsais64_plcp_gsa"
+        rc = self._f(name, bits)(ptr(T), ptr(SA), ptr(P), ct(n))
+        return rc, P[:n]
+
     def sa_int(self, T, k, bits=32, fs=0):
         dt, ct = self._it(bits)
         n = len(T)

@@ -89,3 +89,27 @@ def int_cases():
     c["ramp_down"] = (np.arange(2000, 0, -1), 2001)
     c["period3"] = (np.resize(np.array([5, 5, 9]), 4001), 10)
     return c
+
+
+def gsa_cases():
+    """name -> uint8 array ending in 0: collections of 0-separated strings (libsais_gsa)."""
+    rng = np.random.default_rng(21)
+    c = {}
+    c["kat"] = _b(b"ab\0ab\0b\0")
+    c["only_sep"] = np.zeros(1, dtype=np.uint8)
+    c["one_string"] = _b(b"banana\0")
+    c["dup_strings"] = _b(b"abc\0abc\0abc\0")
+
+    def coll(count, maxlen, sigma):
+        parts = []
+        for _ in range(count):
+            ln = int(rng.integers(1, maxlen))       # the reference rejects empty members
+            parts.append((rng.integers(0, sigma, ln) + 1).astype(np.uint8))
+            parts.append(np.zeros(1, dtype=np.uint8))
+        return np.concatenate(parts)
+    c["coll_small"] = coll(20, 12, 2)
+    c["coll_dna"] = coll(300, 200, 4)
+    c["coll_bytes"] = coll(100, 500, 255)
+    c["coll_many_short"] = coll(5000, 6, 3)
+    c["coll_repeats"] = np.concatenate([np.resize(np.array([1, 2, 1, 3, 0], dtype=np.uint8), 20000)])
+    return c

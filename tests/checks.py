@@ -103,6 +103,35 @@ def check_golden(impl, which=("small", "medium", "int"), bits=32):
     return failures
 
 
+def check_gsa(impl, bits=32):
+    """Generalized SA + PLCP-GSA against the golden vectors (generated from the compiled reference)."""
+    g = golden()["gsa"]
+    dt = np.int32 if bits == 32 else np.int64
+    failures = {}
+    for name, T in cases.gsa_cases().items():
+        gi = g[name]
+        assert digest(T) == gi["input_sha"]
+        bad = []
+        rc, SA, freq = impl.gsa(T, bits, want_freq=True)
+        enc = (lambda a: [int(x) for x in a]) if gi["full"] else (lambda a: digest(a.astype(np.int32)))
+        if rc != 0 or enc(SA) != gi["sa"]:
+            bad.append("gsa")
+        elif digest(freq.astype(np.int32)) != gi["freq"]:
+            bad.append("freq")
+        else:
+            rc, P = impl.plcp_gsa(T, SA.astype(dt), bits)
+            if rc != 0 or enc(P) != gi["plcp"]:
+                bad.append("plcp_gsa")
+        if bad:
+            failures[name] = bad
+    # a collection must end with a separator (reference :7035) and have no empty member (:6886-6889)
+    for bad_text in (b"ab\0ab", b"\0a\0", b"a\0\0", b"ab\0\0cd\0", b"\0\0"):
+        rc, _ = impl.gsa(np.frombuffer(bad_text, dtype=np.uint8).copy(), bits)
+        if rc != -1:
+            failures["rejects:" + repr(bad_text)] = [rc]
+    return failures
+
+
 def check_kat(impl):
     k = kat()
     T = np.frombuffer(k["banana"]["text"].encode(), dtype=np.uint8).copy()
@@ -121,6 +150,11 @@ def check_kat(impl):
     assert rc == 0 and list(SA) == k["a8"]["sa"]
     rc, U = impl.bwt(T)
     assert rc == k["a8"]["primary"]
+    T = np.frombuffer(b"ab\0ab\0b\0", dtype=np.uint8).copy()
+    rc, SA = impl.gsa(T)
+    assert rc == 0 and list(SA) == k["gsa"]["sa"]
+    rc, P = impl.plcp_gsa(T, SA)
+    assert rc == 0 and list(P) == k["gsa"]["plcp"]
     Ti = np.array(k["int"]["text"], dtype=np.int32)
     rc, SA, Tafter = impl.sa_int(Ti, k["int"]["k"])
     assert rc == 0 and list(SA) == k["int"]["sa"] and list(Tafter) == k["int"]["text"]

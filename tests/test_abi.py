@@ -59,12 +59,15 @@ def test_argument_validation_and_fast_paths():
     checks.check_errors(_libs.cuda())
 
 
-def test_gsa_entry_points_link_and_report_unsupported():
-    lib = _libs.cuda().lib
-    T = np.frombuffer(b"ab\0ab\0b\0", dtype=np.uint8).copy()
-    SA = np.zeros(8, dtype=np.int32)
-    lib.libsais_gsa.restype = C.c_int32
-    assert lib.libsais_gsa(_libs.ptr(T), _libs.ptr(SA), C.c_int32(8), C.c_int32(0), None) == -1
+def test_gsa_entry_points_validate_like_the_reference():
+    """GSA needs a trailing separator (reference src/libsais.c:7035); n <= 1 needs no GPU."""
+    cu = _libs.cuda()
+    rc, _ = cu.gsa(np.frombuffer(b"ab\0ab", dtype=np.uint8).copy())
+    assert rc == -1
+    rc, SA = cu.gsa(np.zeros(1, dtype=np.uint8))
+    assert rc == 0 and SA[0] == 0
+    rc, _ = cu.gsa(np.zeros(0, dtype=np.uint8))
+    assert rc == 0
 
 
 def test_no_cpu_fallback_without_gpu():

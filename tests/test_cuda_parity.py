@@ -44,6 +44,23 @@ def test_golden_int_alphabets(cu):
     assert checks.check_golden(cu, which=("int",), bits=64) == {}
 
 
+def test_generalized_suffix_arrays(cu):
+    """libsais_gsa / libsais_plcp_gsa (+64-bit): golden vectors and a larger random collection vs the oracle."""
+    assert checks.check_gsa(cu, 32) == {}
+    assert checks.check_gsa(cu, 64) == {}
+    rng = np.random.default_rng(8)
+    parts = []
+    for _ in range(20000):
+        parts.append((rng.integers(0, 4, int(rng.integers(0, 120))) + 65).astype(np.uint8))
+        parts.append(np.zeros(1, dtype=np.uint8))
+    T = np.concatenate(parts)
+    o = _libs.oracle()
+    a, b = cu.gsa(T), o.gsa(T)
+    assert a[0] == b[0] == 0 and (a[1] == b[1]).all()
+    p1, p2 = cu.plcp_gsa(T, b[1]), o.plcp_gsa(T, b[1])
+    assert p1[0] == p2[0] == 0 and (p1[1] == p2[1]).all()
+
+
 def _full_compare(cu, other, T, bits=32, aux_r=64):
     a, b = cu.sa(T, bits, want_freq=True), other.sa(T, bits, want_freq=True)
     assert a[0] == b[0] == 0
@@ -166,6 +183,31 @@ def test_inplace_aliasing(cu):
     assert rc == rc2 and (U2 == U).all() and U2 is buf
     rc3, back = cu.unbwt(buf, rc, inplace=True)
     assert rc3 == 0 and (back == T).all()
+
+
+def test_concurrent_host_threads_use_independent_contexts(cu):
+    """Re-entrancy: ctx-less calls from different host threads use per-thread contexts and may run
+    concurrently (reference contract: one context per thread, include/libsais.h:53-55)."""
+    import threading
+    o = _libs.oracle()
+    inputs = [gen.dna(40 + i, 300000 + 1111 * i) for i in range(4)] + [gen.rand_bytes(50 + i, 200000 + 77 * i) for i in range(4)]
+    want = [(o.sa(T)[1], o.bwt(T)) for T in inputs]
+    results = [None] * len(inputs)
+
+    def work(i):
+        for _ in range(3):
+            rc, SA = cu.sa(inputs[i])
+            rcb, U = cu.bwt(inputs[i])
+            results[i] = (rc, SA, rcb, U)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(inputs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i, (rc, SA, rcb, U) in enumerate(results):
+        assert rc == 0 and (SA == want[i][0]).all()
+        assert rcb == want[i][1][0] and (U == want[i][1][1]).all()
 
 
 def test_device_pointer_entry_points_roundtrip(cu):

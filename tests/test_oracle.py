@@ -21,6 +21,17 @@ def test_oracle_matches_golden_vectors_64():
     assert checks.check_golden(_libs.oracle(), which=("small", "int"), bits=64) == {}
 
 
+def test_oracle_gsa_matches_golden_vectors():
+    assert checks.check_gsa(_libs.oracle(), 32) == {}
+    assert checks.check_gsa(_libs.oracle(), 64) == {}
+
+
+def test_reference_gsa_reproduces_golden_vectors():
+    if _libs.ref() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    assert checks.check_gsa(_libs.ref(), 32) == {}
+
+
 def test_oracle_error_codes_and_fast_paths():
     checks.check_errors(_libs.oracle())
 
