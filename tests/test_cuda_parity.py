@@ -51,7 +51,7 @@ def test_generalized_suffix_arrays(cu):
     rng = np.random.default_rng(8)
     parts = []
     for _ in range(20000):
-        parts.append((rng.integers(0, 4, int(rng.integers(0, 120))) + 65).astype(np.uint8))
+        parts.append((rng.integers(0, 4, int(rng.integers(1, 120))) + 65).astype(np.uint8))
         parts.append(np.zeros(1, dtype=np.uint8))
     T = np.concatenate(parts)
     o = _libs.oracle()
