@@ -140,6 +140,7 @@ struct PassSmem {
     alignas(16) u32 whist[(THREADS / 32) * kRadixSize];   // zeroed with 16-byte stores
     u32  cnt[kRadixSize];
     u32  scan_tmp[32];
+    alignas(8) u64 mbar[2];                // TMA completion barriers: [0] keys, [1] values
     u32  tile;
 };
 
@@ -149,6 +150,32 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one elected thread moves a
+// whole tile of keys / values from global into shared memory; no per-thread load instructions, no registers.
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    u32 done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
 
 static const int kLookBatch = 8;           // predecessor status words prefetched before the ranking
 static const int kLookRefill = 16;         // words per further round trip
@@ -230,7 +257,7 @@ __device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT
                                                const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
                                                KeyT *__restrict__ kout, ValT *__restrict__ vout,
                                                const u32 tile, const u32 count, int shift, u32 dmask,
-                                               const u64 *__restrict__ base, ST *status, u32 *err)
+                                               const u64 *__restrict__ base, ST *status, u32 *err, const bool use_bulk)
 {
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * IPT;
@@ -238,28 +265,44 @@ __device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT
     const u64 tile_base = (u64)tile * TILE;
     kin += tile_base; vin += tile_base;
 
-    // ---- load keys (+ values), warp-striped: element order inside the tile = (warp, item, lane)
+    // ---- load keys (+ values), warp-striped: element order inside the tile = (warp, item, lane).
+    // Full tiles of 16-byte aligned arrays come in by TMA: one thread issues two bulk copies (keys into the
+    // staging area the sorted tile will later overwrite, values into vals_in); everybody else just waits
+    // on the mbarrier and reads shared memory.
     KeyT key[IPT];
     ValT val[VALS == 1 ? IPT : 1];
     const u32 wbase = warp * (IPT * 32) + lane;
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        u32 li = wbase + i * 32;
-        key[i] = (FULL || li < count) ? (Gen::kActive ? (KeyT)gen.key(tile_base + li) : kin[li]) : (KeyT)0;
-    }
-    if (Gen::kActive) {
-        // values are recomputed at scatter time
-    } else if (VALS == 1) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            u32 li = wbase + i * 32;
-            val[VALS == 1 ? i : 0] = (FULL || li < count) ? vin[li] : (ValT)0;
+    const bool bulk = FULL && VALS == 2 && !Gen::kActive && use_bulk;
+    if (bulk) {
+        if (tid == 0) {
+            mbar_expect_tx(&sm.mbar[0], (u32)(TILE * sizeof(KeyT)));
+            bulk_load(sm.keys, kin, (u32)(TILE * sizeof(KeyT)), &sm.mbar[0]);
+            mbar_expect_tx(&sm.mbar[1], (u32)(TILE * sizeof(ValT)));
+            bulk_load(sm.vals_in, vin, (u32)(TILE * sizeof(ValT)), &sm.mbar[1]);
         }
+        mbar_wait(&sm.mbar[0], 0);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) key[i] = sm.keys[wbase + i * 32];
     } else {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             u32 li = wbase + i * 32;
-            if (FULL || li < count) cp_async4(&sm.vals_in[VALS == 2 ? li : 0], vin + li);
+            key[i] = (FULL || li < count) ? (Gen::kActive ? (KeyT)gen.key(tile_base + li) : kin[li]) : (KeyT)0;
+        }
+        if (Gen::kActive) {
+            // values are recomputed at scatter time
+        } else if (VALS == 1) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                u32 li = wbase + i * 32;
+                val[VALS == 1 ? i : 0] = (FULL || li < count) ? vin[li] : (ValT)0;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                u32 li = wbase + i * 32;
+                if (FULL || li < count) cp_async4(&sm.vals_in[VALS == 2 ? li : 0], vin + li);
+            }
         }
     }
 
@@ -325,8 +368,8 @@ __device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT
         }
     }
     if (VALS == 2 && !Gen::kActive) {
-        cp_async_wait_all();
-        __syncwarp();                                 // a warp reads only the values it fetched itself
+        if (bulk) mbar_wait(&sm.mbar[1], 0); else cp_async_wait_all();
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             u32 li = wbase + i * 32;
@@ -359,7 +402,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : (THREADS <= 512
 sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
                  KeyT *__restrict__ kout, ValT *__restrict__ vout, u64 n,
                  int shift, u32 dmask, const u64 *__restrict__ base,
-                 ST *status, u32 *ticket, u32 *err, const Gen gen)
+                 ST *status, u32 *ticket, u32 *err, const Gen gen, const int use_bulk)
 {
     typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
     constexpr int WARPS = THREADS / 32;
@@ -369,7 +412,11 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
 
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    if (tid == 0) {
+        sm.tile = atomicAdd(ticket, 1u);
+        mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1);
+        mbar_fence_init();
+    }
     {
         uint4 *z = reinterpret_cast<uint4 *>(sm.whist);
         for (int i = tid; i < WARPS * kRadixSize / 4; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
@@ -380,9 +427,9 @@ sort_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     const u64 tile_base = (u64)tile * TILE;
     const u32 count = (u32)((n - tile_base) < (u64)TILE ? (n - tile_base) : (u64)TILE);
     if (count == TILE)
-        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, ST, true, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
+        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, ST, true, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err, use_bulk != 0);
     else
-        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, ST, false, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err);
+        sort_pass_tile<KeyT, ValT, THREADS, IPT, VALS, ST, false, Gen>(sm, gen, kin, vin, kout, vout, tile, count, shift, dmask, base, status, err, false);
 }
 
 // Tile shapes of the pass kernel; LIBSAIS_CUDA_SORT_VARIANT selects one for experiments.
@@ -425,12 +472,16 @@ struct RadixSort {
         typedef PassSmem<KeyT, ValT, THREADS, IPT, VALS> Smem;
         auto kern = sort_pass_kernel<KeyT, ValT, THREADS, IPT, VALS, ST, Gen>;
         ST *status = reinterpret_cast<ST *>(status_raw);
+        // TMA bulk loads need 16-byte aligned sources (tile offsets are multiples of 16 bytes by construction)
+        static const bool bulk_env = [] { const char *e = getenv("LIBSAIS_CUDA_TMA"); return !(e && *e && atoi(e) == 0); }();
+        const int use_bulk = bulk_env && !Gen::kActive && (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0
+                             && ((size_t)THREADS * IPT * sizeof(KeyT)) % 16 == 0 && ((size_t)THREADS * IPT * sizeof(ValT)) % 16 == 0;
         c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         u64 nt = ceil_div(n, (u64)THREADS * IPT);
         const double in_bytes = Gen::kActive ? 2.0 : (double)(sizeof(KeyT) + sizeof(ValT));   // generator: packed text + bwt byte
         const int kc = c.pass_class_override >= 0 ? c.pass_class_override : (Gen::kActive ? KC_SORT_PASS_GEN : KC_SORT_PASS);
         LSC_LAUNCH(c, kc, (double)n * (in_bytes + sizeof(KeyT) + sizeof(ValT)), kern, (u32)nt, THREADS, sizeof(Smem),
-                   kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err, gen);
+                   kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err, gen, use_bulk);
     }
 
     template <int THREADS, int IPT, int VALS, typename Gen>
