@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsais_cuda.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["ctx.cu", "sa_core.cu", "post.cu", "gsa.cu", "api.cu"]
+SOURCES = ["ctx.cu", "hostcopy.cu", "sa_core.cu", "post.cu", "gsa.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("LSC_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
             if log:
                 print(log)
     # API symbols are exported explicitly via the version script; everything else stays hidden
-    cmd = [NVCC, "-shared", "-o", OUT] + [o for o, _ in res] + ["-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map")]
+    cmd = [NVCC, "-shared", "-o", OUT] + [o for o, _ in res] + ["-lpthread", "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -5,6 +5,7 @@
 // reference; all computing is done by the CUDA pipelines -- there is no CPU
 // fallback: without a usable GPU every computing call returns -2.
 #include "core.h"
+#include "hostcopy.h"
 #include <cstring>
 #include <cstdlib>
 #include <new>
@@ -78,7 +79,7 @@ void *upload_text(Ctx &c, const void *h, size_t bytes)
     char *d = (char *)c.alloc(bytes + kPad);
     if (!d) return nullptr;
     c.check(cudaMemsetAsync(d + bytes, 0, kPad, c.stream));
-    c.check(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c.stream));
+    if (!copy_h2d(c, d, h, bytes)) return nullptr;
     return d;
 }
 
@@ -98,11 +99,11 @@ template <typename IDX> void host_freq(const uint8_t *T, IDX n, IDX *freq)
 template <typename IDX> bool download_indexes(Ctx &c, const u32 *d_src, IDX *h_dst, u64 count, void *scratch8)
 {
     if (sizeof(IDX) == 4) {
-        return c.check(cudaMemcpyAsync(h_dst, d_src, count * 4, cudaMemcpyDeviceToHost, c.stream));
+        return copy_d2h(c, h_dst, d_src, count * 4);
     }
     i64 *wide = (i64 *)scratch8;
     run_widen(c, d_src, wide, count);
-    return c.check(cudaMemcpyAsync(h_dst, wide, count * 8, cudaMemcpyDeviceToHost, c.stream));
+    return copy_d2h(c, h_dst, wide, count * 8);
 }
 
 // Host index array (API width) -> device u32 array.
@@ -111,11 +112,11 @@ template <typename IDX> u32 *upload_indexes(Ctx &c, const IDX *h_src, u64 count)
     u32 *d = c.alloc_n<u32>(count);
     if (!d) return nullptr;
     if (sizeof(IDX) == 4) {
-        c.check(cudaMemcpyAsync(d, h_src, count * 4, cudaMemcpyHostToDevice, c.stream));
+        copy_h2d(c, d, h_src, count * 4);
     } else {
         i64 *wide = c.alloc_n<i64>(count);
         if (!wide) return nullptr;
-        c.check(cudaMemcpyAsync(wide, h_src, count * 8, cudaMemcpyHostToDevice, c.stream));
+        copy_h2d(c, wide, h_src, count * 8);
         run_narrow(c, wide, d, count);
     }
     return d;
@@ -246,7 +247,7 @@ IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *f
     if (res.primary < 1 || res.primary > (u64)n) return -2;
     if (run_bwt_finish(*c, d_T, d_rows, d_U, (u64)n, res.primary) != 0) return -2;
     call.stop_timer();
-    c->check(cudaMemcpyAsync(U, d_U, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    copy_d2h(*c, U, d_U, (size_t)n);
     if (n_aux) download_indexes<IDX>(*c, d_I, I, n_aux, res.scratch);
     if (!call.finish()) return -2;
     store_freq(*c, freq);
@@ -274,7 +275,7 @@ IDX unbwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, const IDX *f
     call.start_timer();
     if (run_unbwt(*c, d_B, d_U, (u64)n, (u64)I[0]) != 0) return -2;
     call.stop_timer();
-    c->check(cudaMemcpyAsync(U, d_U, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    copy_d2h(*c, U, d_U, (size_t)n);
     if (!call.finish()) return -2;
     return 0;
 }

@@ -27,6 +27,7 @@ void Ctx::destroy()
     pending.clear();
     for (auto e : event_pool) cudaEventDestroy(e);
     event_pool.clear();
+    free_staging();
     if (ws) cudaFree(ws);
     if (d_scalars) cudaFree(d_scalars);
     if (h_scalars) cudaFreeHost(h_scalars);

@@ -47,6 +47,12 @@ struct Ctx {
     std::vector<RoundStat> rounds;
     float last_device_ms = 0.f;   // first-kernel -> last-kernel device time of the last *_dev call
 
+    // pinned staging lanes for large pageable host transfers (hostcopy.cu)
+    struct StageLane { cudaStream_t stream = nullptr; void *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; };
+    std::vector<StageLane> stage;
+    bool ensure_staging(int workers);
+    void free_staging();
+
     bool init(int dev);
     void destroy();
 
