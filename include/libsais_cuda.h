@@ -73,6 +73,33 @@ int64_t libsais_cuda_lcp_dev(const void * ctx, const uint32_t * d_PLCP, const ui
 /* Inverse BWT; mirrors libsais_unbwt() [:289]. */
 int64_t libsais_cuda_unbwt_dev(const void * ctx, const uint8_t * d_B, uint8_t * d_U, int64_t n, int64_t primary);
 
+/* ---- building blocks of the distributed prefix doubling (texts beyond one GPU's working set; orchestrated by
+ * libsais_b200/dist.py: one process per GPU, torch.distributed / NCCL all-to-alls between these calls).
+ * Device pointers; every call completes before it returns. */
+
+/* Histogram, alphabet map and bit-packing of the (replicated) text; keeps the packed text in the context.
+ * Outputs the symbols per round-0 key and the k-mer width in bits. */
+int64_t libsais_cuda_dist_prepare(const void * ctx, const uint8_t * d_T, int64_t n, int32_t * k_out, int32_t * key_bits_out);
+/* Round-0 keys of positions [lo, lo+count): (k-mer << 7) | length field (127 = full length), and the positions. */
+int64_t libsais_cuda_dist_keys(const void * ctx, int64_t lo, int64_t count, uint64_t * d_keys, uint32_t * d_pos);
+/* Onesweep sort of (u64 key, u32 value) / (u32, u32) pairs on key bits [lo_bit, hi_bit); returns 0 when the
+ * result is in (d_keys, d_vals), 1 when in the alternate buffers, < 0 on error. */
+int64_t libsais_cuda_sort_pairs_dev(const void * ctx, uint64_t * d_keys, uint32_t * d_vals, uint64_t * d_keys_alt, uint32_t * d_vals_alt,
+                                    int64_t count, int32_t lo_bit, int32_t hi_bit);
+int64_t libsais_cuda_sort_u32_pairs_dev(const void * ctx, uint32_t * d_keys, uint32_t * d_vals, uint32_t * d_keys_alt, uint32_t * d_vals_alt,
+                                        int64_t count, int32_t lo_bit, int32_t hi_bit);
+/* Rank stage on a sorted slice whose element j sits in global slot slot_base + j (d_slot_in == NULL) or
+ * d_slot_in[j]: (position, rank) pairs for all elements, the SA slice, the compacted unresolved suffixes;
+ * counts_out[0..1] = unresolved suffixes, unresolved groups. */
+int64_t libsais_cuda_rank_stage_dev(const void * ctx, const uint64_t * d_keys, const uint32_t * d_pos, const uint32_t * d_slot_in,
+                                    int64_t count, uint32_t slot_base, uint32_t * d_sa_local, uint32_t * d_pair_pos, uint32_t * d_pair_rank,
+                                    uint32_t * d_act_pos, uint32_t * d_act_slot, uint32_t * d_act_grp, uint64_t * counts_out);
+/* out[i] = src[idx[i] - idx_offset] (0 when out of range);  dst[idx[i] - idx_offset] = val[i]. */
+int64_t libsais_cuda_gather_u32_dev(const void * ctx, const uint32_t * d_src, int64_t src_len, const uint32_t * d_idx, int64_t count,
+                                    uint32_t idx_offset, uint32_t * d_out);
+int64_t libsais_cuda_scatter_u32_dev(const void * ctx, uint32_t * d_dst, int64_t dst_len, const uint32_t * d_idx, const uint32_t * d_val,
+                                     int64_t count, uint32_t idx_offset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -576,4 +576,87 @@ int64_t libsais_cuda_unbwt_dev(const void *ctx, const uint8_t *d_B, uint8_t *d_U
     return call.finish() ? 0 : -2;
 }
 
+
+// ------------------------------------------------------------------ distributed building blocks
+// (include/libsais_cuda.h; orchestrated by libsais_b200/dist.py with torch.distributed all-to-alls)
+int64_t libsais_cuda_dist_prepare(const void *ctx, const uint8_t *d_T, int64_t n, int32_t *k_out, int32_t *key_bits_out)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (d_T == nullptr || n <= 0 || k_out == nullptr || key_bits_out == nullptr) return -1;
+    Call call(*c);
+    int k = 0, K = 0;
+    int rc = dist_prepare(*c, d_T, (u64)n, &k, &K);
+    *k_out = k; *key_bits_out = K;
+    return rc;
+}
+int64_t libsais_cuda_dist_keys(const void *ctx, int64_t lo, int64_t count, uint64_t *d_keys, uint32_t *d_pos)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (lo < 0 || count < 0 || d_keys == nullptr || d_pos == nullptr) return -1;
+    Call call(*c);
+    int rc = dist_keys(*c, (u64)lo, (u64)count, d_keys, d_pos);
+    return rc == 0 && call.finish() ? 0 : (rc ? rc : -2);
+}
+int64_t libsais_cuda_sort_pairs_dev(const void *ctx, uint64_t *d_keys, uint32_t *d_vals, uint64_t *d_keys_alt, uint32_t *d_vals_alt,
+                                    int64_t count, int32_t lo_bit, int32_t hi_bit)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (count < 0 || lo_bit < 0 || hi_bit > 64 || hi_bit < lo_bit) return -1;
+    if (count == 0) return 0;
+    Call call(*c);
+    if (!c->reserve(sort_workspace_bytes((u64)count) + 4096)) return -2;
+    int where = run_sort_pairs(*c, d_keys, d_vals, d_keys_alt, d_vals_alt, (u64)count, lo_bit, hi_bit);
+    return where >= 0 && call.finish() ? where : -2;
+}
+int64_t libsais_cuda_sort_u32_pairs_dev(const void *ctx, uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_keys_alt, uint32_t *d_vals_alt,
+                                        int64_t count, int32_t lo_bit, int32_t hi_bit)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (count < 0 || lo_bit < 0 || hi_bit > 32 || hi_bit < lo_bit) return -1;
+    if (count == 0) return 0;
+    Call call(*c);
+    if (!c->reserve(sort_workspace_bytes((u64)count) + 4096)) return -2;
+    int where = run_sort_u32_pairs(*c, d_keys, d_vals, d_keys_alt, d_vals_alt, (u64)count, lo_bit, hi_bit);
+    return where >= 0 && call.finish() ? where : -2;
+}
+int64_t libsais_cuda_rank_stage_dev(const void *ctx, const uint64_t *d_keys, const uint32_t *d_pos, const uint32_t *d_slot_in,
+                                    int64_t count, uint32_t slot_base, uint32_t *d_sa_local, uint32_t *d_pair_pos, uint32_t *d_pair_rank,
+                                    uint32_t *d_act_pos, uint32_t *d_act_slot, uint32_t *d_act_grp, uint64_t *counts_out)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (count < 0 || counts_out == nullptr) return -1;
+    Call call(*c);
+    if (!c->reserve(rank_stage_workspace_bytes((u64)count) + 4096)) return -2;
+    u64 counts[2] = {0, 0};
+    int rc = run_rank_stage(*c, d_keys, d_pos, d_slot_in, (u64)count, slot_base, d_sa_local, d_pair_pos, d_pair_rank,
+                            d_act_pos, d_act_slot, d_act_grp, counts);
+    counts_out[0] = counts[0]; counts_out[1] = counts[1];
+    return rc == 0 && call.finish() ? 0 : -2;
+}
+int64_t libsais_cuda_gather_u32_dev(const void *ctx, const uint32_t *d_src, int64_t src_len, const uint32_t *d_idx, int64_t count,
+                                    uint32_t idx_offset, uint32_t *d_out)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (count < 0 || src_len < 0) return -1;
+    Call call(*c);
+    run_gather_u32(*c, d_src, (u64)src_len, d_idx, (u64)count, idx_offset, d_out);
+    return call.finish() ? 0 : -2;
+}
+int64_t libsais_cuda_scatter_u32_dev(const void *ctx, uint32_t *d_dst, int64_t dst_len, const uint32_t *d_idx, const uint32_t *d_val,
+                                     int64_t count, uint32_t idx_offset)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (count < 0 || dst_len < 0) return -1;
+    Call call(*c);
+    run_scatter_u32(*c, d_dst, (u64)dst_len, d_idx, d_val, (u64)count, idx_offset);
+    return call.finish() ? 0 : -2;
+}
+
 }  // extern "C"

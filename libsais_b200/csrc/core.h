@@ -60,6 +60,19 @@ int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary);
 size_t gsa_workspace_bytes(u64 n);
 u32 *build_gsa_text(Ctx &c, const u8 *d_T, u64 n);
 
+// building blocks of the distributed prefix doubling (sa_core.cu)
+int dist_prepare(Ctx &c, const u8 *d_T, u64 n, int *k_out, int *K_out);
+int dist_keys(Ctx &c, u64 lo, u64 count, u64 *d_keys, u32 *d_pos);
+size_t rank_stage_workspace_bytes(u64 count);
+int run_rank_stage(Ctx &c, const u64 *d_keys, const u32 *d_pos, const u32 *d_slot_in, u64 count, u32 slot_base,
+                   u32 *d_sa_local, u32 *d_pair_pos, u32 *d_pair_rank, u32 *d_act_pos, u32 *d_act_slot, u32 *d_act_grp,
+                   u64 *counts);
+size_t sort_workspace_bytes(u64 count);
+int run_sort_pairs(Ctx &c, u64 *ka, u32 *va, u64 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit);
+int run_sort_u32_pairs(Ctx &c, u32 *ka, u32 *va, u32 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit);
+void run_gather_u32(Ctx &c, const u32 *src, u64 src_len, const u32 *idx, u64 count, u32 idx_offset, u32 *out);
+void run_scatter_u32(Ctx &c, u32 *dst, u64 dst_len, const u32 *idx, const u32 *val, u64 count, u32 idx_offset);
+
 // conversions used by the 64-bit API
 void run_widen(Ctx &c, const u32 *src, i64 *dst, u64 n);
 void run_narrow(Ctx &c, const i64 *src, u32 *dst, u64 n);

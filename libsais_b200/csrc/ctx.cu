@@ -28,6 +28,7 @@ void Ctx::destroy()
     for (auto e : event_pool) cudaEventDestroy(e);
     event_pool.clear();
     free_staging();
+    if (dist_words) { cudaFree(dist_words); dist_words = nullptr; }
     if (ws) cudaFree(ws);
     if (d_scalars) cudaFree(d_scalars);
     if (h_scalars) cudaFreeHost(h_scalars);

@@ -47,6 +47,9 @@ struct Ctx {
     std::vector<RoundStat> rounds;
     float last_device_ms = 0.f;   // first-kernel -> last-kernel device time of the last *_dev call
 
+    // distributed building blocks: packed text kept across calls (sa_core.cu dist_prepare)
+    u64 *dist_words = nullptr; u64 dist_n = 0; int dist_b = 0, dist_k = 0;
+
     // pinned staging lanes for large pageable host transfers (hostcopy.cu)
     struct StageLane { cudaStream_t stream = nullptr; void *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; };
     std::vector<StageLane> stage;

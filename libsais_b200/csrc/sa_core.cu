@@ -170,7 +170,8 @@ __device__ __forceinline__ u64 ceil_div_dev(u64 a, u64 b) { return (a + b - 1) /
 struct RankArgs {
     const u64 *keys; const u32 *pos; const u32 *slot_in;
     u64 N; u64 tail_start; int key_shift;
-    u32 *SA;                 // nullable: SA[slot] = pos
+    u32 slot_base;           // global slot of element 0 (0 on one GPU; a rank's offset in the distributed sort)
+    u32 *SA;                 // nullable: SA[slot - slot_base] = pos
     u32 *ISA; int isa_all;   // isa_all: write every element's rank, else only the active ones
     u32 *pair_idx, *pair_val; // non-null: emit (position, rank) pairs in element order instead of scattering into ISA
     u8 *rows; const u8 *text;            // BWT mode: rows[slot] = byte preceding the suffix
@@ -205,7 +206,7 @@ rank_flags_kernel(const RankArgs a)
         const u64 kraw = valid ? a.keys[j] : 0;
         kk[i] = kraw >> a.key_shift;
         p[i] = valid ? a.pos[j] : 0;
-        slot[i] = ROUND0 ? (u32)j : (valid ? a.slot_in[j] : 0);
+        slot[i] = ROUND0 ? a.slot_base + (u32)j : (valid ? a.slot_in[j] : 0);
         if (ROUND0) pc[i >> 2] |= (u32)(kraw & 255) << (8 * (i & 3));
     }
     const u64 jfirst = wbase - lane, jlast = jfirst + kRankIPT * 32;      // chunk = [jfirst, jlast)
@@ -268,7 +269,7 @@ rank_flags_kernel(const RankArgs a)
         }
         if (valid) {
             const bool act = (am >> lane) & 1;
-            if (a.SA) a.SA[slot[i]] = p[i];
+            if (a.SA) a.SA[slot[i] - a.slot_base] = p[i];
             if (a.rows) {
                 if (ROUND0) a.rows[slot[i]] = (u8)(pc[i >> 2] >> (8 * (i & 3)));
                 else if (!act && p[i] != 0) a.rows[slot[i]] = a.text[p[i] - 1];
@@ -388,7 +389,7 @@ rank_apply_kernel(const RankArgs a)
         const bool cv = chunk < a.nchunks;
         hm[i] = cv ? a.masks[chunk] : 0; am[i] = cv ? a.masks[a.nchunks + chunk] : 0; gm[i] = cv ? a.masks[2 * a.nchunks + chunk] : 0;
         p[i] = valid ? a.pos[j] : 0;
-        slot[i] = ROUND0 ? (u32)j : (valid ? a.slot_in[j] : 0);
+        slot[i] = ROUND0 ? a.slot_base + (u32)j : (valid ? a.slot_in[j] : 0);
     }
 #pragma unroll
     for (int i = 0; i < kRankIPT; ++i) {
@@ -676,6 +677,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
 
     RankArgs ra;
     ra.keys = ks; ra.pos = vs; ra.slot_in = nullptr; ra.N = n; ra.tail_start = tail_start; ra.key_shift = key_shift;
+    ra.slot_base = 0;
     ra.SA = SA; ra.ISA = ISA; ra.isa_all = 0;
     ra.rows = bwt_mode ? opt.bwt_rows : nullptr; ra.text = bwt_mode ? (const u8 *)d_T : nullptr;
     ra.aux_I = opt.aux_I; ra.aux_mask = opt.aux_I ? opt.aux_r - 1 : 0; ra.aux_shift = opt.aux_I ? bits_for(opt.aux_r) - 1 : 0;
@@ -754,6 +756,155 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     out->primary = c.h_scalars[S_PRIMARY];
     out->scratch = keyA; out->scratch_bytes = (size_t)n * 8;
     return c.failed() ? -2 : 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Building blocks of the distributed prefix doubling (libsais_b200/dist.py): the
+// text is replicated, every rank owns a range of positions (ISA slice) and, after the sample
+// sort, a range of keys (a slice of the sorted order).  The kernels are the single-GPU ones; the
+// exchanges between them are NCCL all-to-alls issued from the host side.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dist_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int k, int K, u64 lo, u64 count,
+                 u64 *__restrict__ keys, u32 *__restrict__ pos)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    u64 p = lo + i;
+    // the length field makes suffixes that run past the end unique and orders them before every
+    // longer suffix with the same zero-padded k-mer: no stability is asked of the distributed sort
+    u64 len = p + (u64)k <= n ? 127 : n - p;
+    keys[i] = (kmer_at(words, p, b, K) << 7) | len;
+    pos[i] = (u32)p;
+}
+
+int dist_prepare(Ctx &c, const u8 *d_T, u64 n, int *k_out, int *K_out)
+{
+    if (n == 0 || n > kMaxN) return -2;
+    cudaStream_t st = c.stream;
+    run_byte_histogram(c, d_T, n);
+    c.check(cudaMemcpyAsync(c.h_scalars + S_FREQ, c.d_scalars + S_FREQ, 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (!c.sync()) return -2;
+    u8 *h_lut = (u8 *)(c.h_scalars + S_MISC);
+    int sigma = 0; double entropy = 0;
+    for (int s = 0; s < 256; ++s) {
+        u64 f = c.h_scalars[S_FREQ + s];
+        h_lut[s] = (u8)sigma;
+        if (f) { ++sigma; double pr = (double)f / (double)n; entropy -= pr * std::log2(pr); }
+    }
+    const int b = bits_for((u64)(sigma > 1 ? sigma - 1 : 1));
+    const int k = choose_key_symbols(n, b, entropy, 56);
+    const u64 nwords = ceil_div(n * (u64)b, 64) + 2;
+    if (c.dist_words) { cudaFree(c.dist_words); c.dist_words = nullptr; }
+    if (cudaMalloc(&c.dist_words, nwords * 8 + 256) != cudaSuccess) { cudaGetLastError(); return -2; }
+    u8 *d_lut = (u8 *)(c.dist_words + nwords);
+    c.check(cudaMemcpyAsync(d_lut, h_lut, 256, cudaMemcpyHostToDevice, st));
+    LSC_LAUNCH(c, KC_PACK, (double)n + (double)nwords * 8, (pack_kernel<u8, true>), (u32)ceil_div(nwords, 256), 256, 0, d_T, n, b, c.dist_words, nwords, d_lut);
+    c.dist_n = n; c.dist_b = b; c.dist_k = k;
+    *k_out = k; *K_out = k * b;
+    return c.sync() && !c.failed() ? 0 : -2;
+}
+
+int dist_keys(Ctx &c, u64 lo, u64 count, u64 *d_keys, u32 *d_pos)
+{
+    if (!c.dist_words || lo + count > c.dist_n) return -1;
+    if (count) LSC_LAUNCH(c, KC_MAKE_KEYS, (double)count * 13, dist_keys_kernel, (u32)ceil_div(count, 256), 256, 0,
+                          c.dist_words, c.dist_n, c.dist_b, c.dist_k, c.dist_k * c.dist_b, lo, count, d_keys, d_pos);
+    return c.failed() ? -2 : 0;
+}
+
+size_t rank_stage_workspace_bytes(u64 count)
+{
+    const u64 tiles = ceil_div(count, kRankTile);
+    return 3 * ceil_div(count, 32) * 4 + tiles * (kRankWarps + 1) * 3 * 4 + 4096;
+}
+
+// Rank stage on a sorted slice: element j sits in global slot slot_base + j (slot_in == nullptr) or
+// slot_in[j].  Emits (pos, rank) pairs for every element, the slice of the suffix array, and the
+// compacted active suffixes.  counts[0..1] (host) = active suffixes, active groups.
+int run_rank_stage(Ctx &c, const u64 *d_keys, const u32 *d_pos, const u32 *d_slot_in, u64 count, u32 slot_base,
+                   u32 *d_sa_local, u32 *d_pair_pos, u32 *d_pair_rank, u32 *d_act_pos, u32 *d_act_slot, u32 *d_act_grp,
+                   u64 *counts)
+{
+    counts[0] = counts[1] = 0;
+    if (count == 0) return 0;
+    const u64 tiles = ceil_div(count, kRankTile);
+    u32 *masks = c.alloc_n<u32>(3 * ceil_div(count, 32));
+    u32 *wagg = c.alloc_n<u32>(tiles * kRankWarps * 3);
+    u32 *tagg = c.alloc_n<u32>(tiles * 3);
+    if (!masks || !wagg || !tagg) return -2;
+    RankArgs ra;
+    ra.keys = d_keys; ra.pos = d_pos; ra.slot_in = d_slot_in; ra.N = count; ra.tail_start = ~0ull; ra.key_shift = 0;
+    ra.slot_base = slot_base;
+    ra.SA = d_sa_local; ra.ISA = nullptr; ra.isa_all = 1; ra.pair_idx = d_pair_pos; ra.pair_val = d_pair_rank;
+    ra.rows = nullptr; ra.text = nullptr; ra.aux_mask = 0; ra.aux_shift = 0; ra.aux_I = nullptr;
+    ra.primary = c.d_scalars + S_PRIMARY;
+    ra.a_pos = d_act_pos; ra.a_slot = d_act_slot; ra.a_grp = d_act_grp;
+    ra.masks = masks; ra.wagg = wagg; ra.tagg = tagg; ra.nchunks = ceil_div(count, 32); ra.ntiles = tiles;
+    ra.out_counts = c.d_scalars + S_NACT;
+    if (d_slot_in == nullptr) {
+        LSC_LAUNCH(c, KC_RANK_INIT, (double)count * 16, rank_flags_kernel<true>, (u32)tiles, kRankThreads, 0, ra);
+        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, 1, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
+        LSC_LAUNCH(c, KC_RANK_INIT, (double)count * 24, rank_apply_kernel<true>, (u32)tiles, kRankThreads, 0, ra);
+    } else {
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)count * 20, rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, 1, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)count * 28, rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+    }
+    c.check(cudaMemcpyAsync(c.h_scalars + S_NACT, c.d_scalars + S_NACT, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c.stream));
+    if (!c.sync() || c.failed()) return -2;
+    counts[0] = c.h_scalars[S_NACT]; counts[1] = c.h_scalars[S_NGRP];
+    return 0;
+}
+
+size_t sort_workspace_bytes(u64 count) { return RadixSort<u64, u32>::temp_bytes(count) + 4096; }
+
+int run_sort_pairs(Ctx &c, u64 *ka, u32 *va, u64 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit)
+{
+    void *temp = c.alloc(RadixSort<u64, u32>::temp_bytes(count));
+    if (!temp) return -2;
+    u32 *err = (u32 *)(c.d_scalars + S_ERR);
+    c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, sizeof(u64), c.stream));
+    int where = RadixSort<u64, u32>::sort(c, ka, va, kb, vb, count, lo_bit, hi_bit, temp, err);
+    return where < 0 ? -2 : where;
+}
+
+int run_sort_u32_pairs(Ctx &c, u32 *ka, u32 *va, u32 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit)
+{
+    void *temp = c.alloc(RadixSort<u32, u32>::temp_bytes(count));
+    if (!temp) return -2;
+    u32 *err = (u32 *)(c.d_scalars + S_ERR);
+    c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, sizeof(u64), c.stream));
+    c.pass_class_override = KC_SCATTER;
+    int where = RadixSort<u32, u32>::sort(c, ka, va, kb, vb, count, lo_bit, hi_bit, temp, err);
+    c.pass_class_override = -1;
+    return where < 0 ? -2 : where;
+}
+
+__global__ void __launch_bounds__(256)
+gather_u32_kernel(const u32 *__restrict__ src, u64 src_len, const u32 *__restrict__ idx, u64 count, u32 idx_offset, u32 *__restrict__ out)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    u64 j = (u64)(idx[i] - idx_offset);
+    out[i] = j < src_len ? src[j] : 0;
+}
+__global__ void __launch_bounds__(256)
+scatter_u32_kernel(u32 *__restrict__ dst, u64 dst_len, const u32 *__restrict__ idx, const u32 *__restrict__ val, u64 count, u32 idx_offset)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    u64 j = (u64)(idx[i] - idx_offset);
+    if (j < dst_len) dst[j] = val[i];
+}
+void run_gather_u32(Ctx &c, const u32 *src, u64 src_len, const u32 *idx, u64 count, u32 idx_offset, u32 *out)
+{
+    if (count) LSC_LAUNCH(c, KC_ROUND_KEYS, (double)count * 12, gather_u32_kernel, (u32)ceil_div(count, 256), 256, 0, src, src_len, idx, count, idx_offset, out);
+}
+void run_scatter_u32(Ctx &c, u32 *dst, u64 dst_len, const u32 *idx, const u32 *val, u64 count, u32 idx_offset)
+{
+    if (count) LSC_LAUNCH(c, KC_SCATTER, (double)count * 12, scatter_u32_kernel, (u32)ceil_div(count, 256), 256, 0, dst, dst_len, idx, val, count, idx_offset);
 }
 
 }  // namespace lsc

@@ -1,0 +1,240 @@
+"""Distributed prefix doubling: suffix array of ONE text across several GPUs (BASELINE config 5's
+mechanism).  One process per GPU; torch.distributed (NCCL over
+NVLink) carries the exchanges; all sorting / ranking is done by the library's own kernels through
+the device-pointer building blocks of include/libsais_cuda.h.
+
+Layout: the text is replicated on every rank.  Rank r owns
+  * positions [r*B, (r+1)*B)  -> its slice of ISA (rank of every suffix that starts there), and
+  * after the round-0 sample sort, a contiguous range of KEYS -> a contiguous slice of the sorted
+    order (global slots [base_r, base_r + m_r)): its slice of the final suffix array.
+Equal keys never straddle ranks, so every group of tied suffixes lives on one rank and the
+single-GPU rank stage applies unchanged.  Per round there are three all-to-alls:
+  requests (p + h) to the position owners, their ISA values back, and the new (position, rank)
+  pairs to the position owners.
+Round-1 limit: positions are u32 (n < 2^32 - 16): texts larger than one GPU's ~50 B/suffix working
+set but below 4 Gi symbols.  2^34 symbols (config 5 proper) needs 64-bit positions -- round 2.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import load_library
+
+_M32 = 0xFFFFFFFF
+
+
+def _u32(t):
+    """int32 tensor holding u32 bit patterns -> non-negative int64."""
+    return t.long() & _M32
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr() if t is not None and t.numel() > 0 else (t.data_ptr() if t is not None else 0))
+
+
+def _bits(x):
+    b = 0
+    while x:
+        b += 1
+        x >>= 1
+    return max(b, 1)
+
+
+class _Lib:
+    def __init__(self):
+        lib = load_library()
+        vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+        lib.libsais_cuda_dist_prepare.restype = i64
+        lib.libsais_cuda_dist_prepare.argtypes = [vp, vp, i64, C.POINTER(i32), C.POINTER(i32)]
+        lib.libsais_cuda_dist_keys.restype = i64
+        lib.libsais_cuda_dist_keys.argtypes = [vp, i64, i64, vp, vp]
+        lib.libsais_cuda_sort_pairs_dev.restype = i64
+        lib.libsais_cuda_sort_pairs_dev.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32]
+        lib.libsais_cuda_sort_u32_pairs_dev.restype = i64
+        lib.libsais_cuda_sort_u32_pairs_dev.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32]
+        lib.libsais_cuda_rank_stage_dev.restype = i64
+        lib.libsais_cuda_rank_stage_dev.argtypes = [vp, vp, vp, vp, i64, u32, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
+        lib.libsais_cuda_gather_u32_dev.restype = i64
+        lib.libsais_cuda_gather_u32_dev.argtypes = [vp, vp, i64, vp, i64, u32, vp]
+        lib.libsais_cuda_scatter_u32_dev.restype = i64
+        lib.libsais_cuda_scatter_u32_dev.argtypes = [vp, vp, i64, vp, vp, i64, u32]
+        self.lib = lib
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise RuntimeError("libsais_cuda %s failed: %d" % (what, rc))
+    return rc
+
+
+def _exchange(send, send_counts, world):
+    """all_to_all of variable-sized segments of `send` (segments ordered by destination)."""
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=send.device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc)
+    recv_counts = [int(x) for x in rc.tolist()]
+    out = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(out, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts))
+    return out, recv_counts
+
+
+def _exchange_known(send, send_counts, recv_counts):
+    out = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(out, send, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts))
+    return out
+
+
+class DistributedSA:
+    """Builds the suffix array of a replicated device text `dT` (uint8, n symbols) across the
+    process group.  After run(): self.sa_local (int32 tensor, u32 bit patterns) holds global
+    slots [self.base, self.base + len(self.sa_local)) of the suffix array."""
+
+    def __init__(self, ctx, dT, n, samples=8192):
+        self.L = _Lib().lib
+        self.ctx, self.h = ctx, ctx.handle
+        self.dT, self.n = dT, int(n)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.dev = dT.device
+        self.samples = samples
+        self.B = (self.n + self.world - 1) // self.world          # positions per owner
+        self.lo = min(self.n, self.rank * self.B)
+        self.hi = min(self.n, self.lo + self.B)
+        self.rounds = []
+
+    # ---- helpers -------------------------------------------------------------------------
+    def _sort_pairs(self, keys, vals, lo_bit, hi_bit):
+        ka, va = torch.empty_like(keys), torch.empty_like(vals)
+        w = _check(self.L.libsais_cuda_sort_pairs_dev(self.h, keys.data_ptr(), vals.data_ptr(), ka.data_ptr(), va.data_ptr(),
+                                                      keys.numel(), lo_bit, hi_bit), "sort_pairs")
+        return (ka, va) if w == 1 else (keys, vals)
+
+    def _route(self, owner, payloads):
+        """Group items by destination rank `owner` (int32, values in [0, world]; world = drop) with the
+        library's stable partition pass; returns the permuted payloads and the per-destination counts."""
+        cnt = keys = None
+        nitems = owner.numel()
+        counts = torch.bincount(owner.long(), minlength=self.world + 1)[: self.world + 1].tolist()
+        outs = []
+        obits = _bits(self.world)
+        for p in payloads:
+            k = owner.clone()
+            v = p.clone()
+            ka, va = torch.empty_like(k), torch.empty_like(v)
+            w = _check(self.L.libsais_cuda_sort_u32_pairs_dev(self.h, k.data_ptr(), v.data_ptr(), ka.data_ptr(), va.data_ptr(),
+                                                              nitems, 0, obits), "route")
+            outs.append(va if w == 1 else v)
+        return outs, [int(c) for c in counts[: self.world]]
+
+    def _owner_of(self, pos64):
+        return torch.clamp(pos64 // self.B, max=self.world - 1).to(torch.int32)
+
+    def _scatter_isa(self, pos, rank):
+        """Route (position, rank) pairs to the owners of the positions and store them in the ISA slices."""
+        owner = self._owner_of(_u32(pos))
+        (pos_s, rank_s), counts = self._route(owner, [pos, rank])
+        pos_r, rc = _exchange(pos_s, counts, self.world)
+        rank_r = _exchange_known(rank_s, counts, rc)
+        if pos_r.numel():
+            _check(self.L.libsais_cuda_scatter_u32_dev(self.h, self.isa.data_ptr(), self.isa.numel(), pos_r.data_ptr(), rank_r.data_ptr(),
+                                                       pos_r.numel(), self.lo), "scatter")
+
+    # ---- the algorithm -------------------------------------------------------------------
+    def run(self):
+        n, world, dev = self.n, self.world, self.dev
+        k_out, kb_out = C.c_int32(0), C.c_int32(0)
+        _check(self.L.libsais_cuda_dist_prepare(self.h, self.dT.data_ptr(), n, C.byref(k_out), C.byref(kb_out)), "dist_prepare")
+        k, K = k_out.value, kb_out.value
+        key_bits = K + 7
+        cnt = self.hi - self.lo
+        self.isa = torch.zeros(max(cnt, 1), dtype=torch.int32, device=dev)
+
+        # ---- round 0: keys of the owned positions, sample sort over the ranks
+        keys = torch.empty(max(cnt, 1), dtype=torch.int64, device=dev)[:cnt]
+        pos = torch.empty(max(cnt, 1), dtype=torch.int32, device=dev)[:cnt]
+        _check(self.L.libsais_cuda_dist_keys(self.h, self.lo, cnt, keys.data_ptr(), pos.data_ptr()), "dist_keys")
+        keys, pos = self._sort_pairs(keys, pos, 0, key_bits)
+        # splitters: regular samples of every rank's sorted keys (keys are < 2^63: signed order = unsigned order)
+        ns = min(self.samples, max(cnt, 1))
+        idx = (torch.arange(ns, device=dev, dtype=torch.int64) * max(cnt, 1)) // ns
+        mine = keys[idx] if cnt else torch.full((ns,), (1 << 62), dtype=torch.int64, device=dev)
+        if mine.numel() < self.samples:
+            mine = torch.cat([mine, mine[-1:].expand(self.samples - mine.numel())])
+        allsamp = torch.empty(self.samples * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allsamp, mine.contiguous())
+        allsamp, _ = torch.sort(allsamp)                                  # 8192*G values: plumbing, not the data path
+        splitters = allsamp[[(i * allsamp.numel()) // world for i in range(1, world)]] if world > 1 else allsamp[:0]
+        # destination of a key = number of splitters <= key: equal keys share a destination
+        bounds = torch.searchsorted(keys, splitters, right=False) if world > 1 else keys.new_zeros(0)
+        edges = [0] + [int(x) for x in bounds.tolist()] + [cnt]
+        counts = [edges[i + 1] - edges[i] for i in range(world)]
+        keys_r, rc = _exchange(keys, counts, world)
+        pos_r = _exchange_known(pos, counts, rc)
+        m = keys_r.numel()
+        keys_r, pos_r = self._sort_pairs(keys_r, pos_r, 0, key_bits)      # merge of the received sorted runs
+        sizes = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([m], dtype=torch.int64, device=dev))
+        sizes = sizes.tolist()
+        self.base = int(sum(sizes[: self.rank]))
+        self.sa_local = torch.empty(max(m, 1), dtype=torch.int32, device=dev)[:m]
+
+        act_pos, act_slot, act_grp, n_act, n_grp = self._rank_stage(keys_r, pos_r, None, m)
+        del keys_r, pos_r, keys, pos
+        self.rounds.append({"h": 0, "local": m, "active_local": n_act})
+
+        # ---- doubling rounds
+        rank_bits = _bits(n)
+        h = k
+        while True:
+            tot = torch.tensor([n_act], dtype=torch.int64, device=dev)
+            dist.all_reduce(tot)
+            if int(tot.item()) == 0:
+                break
+            # k2 = ISA[p + h] + 1 (0 past the end): request / response all-to-all with the position owners
+            q = _u32(act_pos) + h
+            valid = q < n
+            owner = torch.where(valid, torch.clamp(q // self.B, max=world - 1), torch.full_like(q, world)).to(torch.int32)
+            ident = torch.arange(n_act, dtype=torch.int32, device=dev)
+            (q_s, id_s), counts = self._route(owner, [q.to(torch.int32), ident])
+            nreq = sum(counts)
+            req, rc = _exchange(q_s[:nreq].contiguous(), counts, world)
+            ans = torch.empty(max(req.numel(), 1), dtype=torch.int32, device=dev)[: req.numel()]
+            if req.numel():
+                _check(self.L.libsais_cuda_gather_u32_dev(self.h, self.isa.data_ptr(), self.isa.numel(), req.data_ptr(), req.numel(),
+                                                          self.lo, ans.data_ptr()), "gather")
+            resp = _exchange_known(ans, rc, counts)
+            k2 = torch.zeros(max(n_act, 1), dtype=torch.int64, device=dev)[:n_act]
+            if nreq:
+                k2[id_s[:nreq].long()] = _u32(resp) + 1
+            grp_bits = _bits(max(n_grp - 1, 1))
+            keys = (_u32(act_grp) << rank_bits) | k2
+            keys, spos = self._sort_pairs(keys, act_pos.clone(), 0, rank_bits + grp_bits)
+            act_pos, act_slot, act_grp, n_act_new, n_grp = self._rank_stage(keys, spos, act_slot, n_act)
+            self.rounds.append({"h": h, "local": n_act, "active_local": n_act_new})
+            n_act = n_act_new
+            h *= 2
+            if len(self.rounds) > 80:
+                raise RuntimeError("distributed prefix doubling did not converge")
+        return self.sa_local, self.base
+
+    def _rank_stage(self, keys, pos, slot_in, count):
+        dev = self.dev
+        pair_pos = torch.empty(max(count, 1), dtype=torch.int32, device=dev)
+        pair_rank = torch.empty(max(count, 1), dtype=torch.int32, device=dev)
+        a_pos = torch.empty(max(count, 1), dtype=torch.int32, device=dev)
+        a_slot = torch.empty(max(count, 1), dtype=torch.int32, device=dev)
+        a_grp = torch.empty(max(count, 1), dtype=torch.int32, device=dev)
+        counts = (C.c_uint64 * 2)()
+        _check(self.L.libsais_cuda_rank_stage_dev(self.h, keys.data_ptr(), pos.data_ptr(), slot_in.data_ptr() if slot_in is not None else None,
+                                                  count, self.base & _M32, self.sa_local.data_ptr(), pair_pos.data_ptr(), pair_rank.data_ptr(),
+                                                  a_pos.data_ptr(), a_slot.data_ptr(), a_grp.data_ptr(), counts), "rank_stage")
+        n_act, n_grp = int(counts[0]), int(counts[1])
+        self._scatter_isa(pair_pos[:count], pair_rank[:count])
+        return a_pos[:n_act].clone(), a_slot[:n_act].clone(), a_grp[:n_act].clone(), n_act, n_grp
+
+
+def distributed_suffix_array(ctx, dT, n):
+    """Convenience wrapper: returns (sa_local, base, rounds)."""
+    d = DistributedSA(ctx, dT, n)
+    sa, base = d.run()
+    return sa, base, d.rounds
