@@ -29,10 +29,6 @@ def _u32(t):
     return t.long() & _M32
 
 
-def _ptr(t):
-    return C.c_void_p(t.data_ptr() if t is not None and t.numel() > 0 else (t.data_ptr() if t is not None else 0))
-
-
 def _bits(x):
     b = 0
     while x:
@@ -141,6 +137,15 @@ class DistributedSA:
 
     # ---- the algorithm -------------------------------------------------------------------
     def run(self):
+        # torch's glue ops and the NCCL collectives are issued on the context's own stream, so they are
+        # ordered with the library's kernels without host synchronisation
+        torch.cuda.current_stream(self.dev).synchronize()
+        with torch.cuda.stream(torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)):
+            out = self._run()
+        torch.cuda.current_stream(self.dev).wait_stream(torch.cuda.ExternalStream(self.ctx.stream, device=self.dev))
+        return out
+
+    def _run(self):
         n, world, dev = self.n, self.world, self.dev
         k_out, kb_out = C.c_int32(0), C.c_int32(0)
         _check(self.L.libsais_cuda_dist_prepare(self.h, self.dT.data_ptr(), n, C.byref(k_out), C.byref(kb_out)), "dist_prepare")

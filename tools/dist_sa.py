@@ -50,6 +50,11 @@ def main():
         full = torch.empty(n, dtype=torch.int32, device="cuda")
         assert ctx.sa_dev(dT.data_ptr(), full.data_ptr(), n) == 0
         ok = bool(torch.equal(full[base: base + sa.numel()], sa))
+        if not ok:
+            ref = full[base: base + sa.numel()]
+            bad = (ref != sa).nonzero().flatten()
+            print("rank", rank, "base", base, "m", sa.numel(), "mismatches", bad.numel(), "first", bad[:5].tolist(),
+                  "got", sa[bad[:5]].tolist(), "want", ref[bad[:5]].tolist(), flush=True)
         flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN); ok = bool(flag.item())
     sizes = [None] * world
     dist.all_gather_object(sizes, int(sa.numel()))
