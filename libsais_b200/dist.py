@@ -238,6 +238,48 @@ class DistributedSA:
         return a_pos[:n_act].clone(), a_slot[:n_act].clone(), a_grp[:n_act].clone(), n_act, n_grp
 
 
+def verify_distributed(d, pairs=200000, depth=256, seed=1):
+    """Checks a DistributedSA result without a single-GPU reference: (1) the slices together are a
+    permutation of [0, n) (positions routed to their owners, every owner sees each of its positions
+    exactly once); (2) sampled adjacent suffixes inside every slice are in order (direct comparison of
+    up to `depth` symbols of the replicated text; undecided pairs are reported, not failed).
+    Returns (ok, info) on every rank."""
+    dev, n, world = d.dev, d.n, d.world
+    with torch.cuda.stream(torch.cuda.ExternalStream(d.ctx.stream, device=dev)):
+        sa = d.sa_local
+        owner = d._owner_of(_u32(sa))
+        (pos_s,), counts = d._route(owner, [sa])
+        got, _ = _exchange(pos_s, counts, world)
+        cnt = d.hi - d.lo
+        seen = torch.zeros(max(cnt, 1), dtype=torch.int32, device=dev)
+        if got.numel():
+            seen.index_put_(((_u32(got) - d.lo),), torch.ones(got.numel(), dtype=torch.int32, device=dev), accumulate=True)
+        perm_ok = bool(got.numel() == cnt and (cnt == 0 or bool((seen[:cnt] == 1).all())))
+        m = sa.numel()
+        bad = undecided = 0
+        if m > 1:
+            g = torch.Generator(device=dev); g.manual_seed(seed + d.rank)
+            i = torch.randint(1, m, (min(pairs, m - 1),), device=dev, generator=g)
+            a, b = _u32(sa[i - 1]), _u32(sa[i])
+            off = torch.arange(depth, device=dev, dtype=torch.int64)
+            ia, ib = a[:, None] + off[None, :], b[:, None] + off[None, :]
+            ta = torch.where(ia < n, d.dT[torch.clamp(ia, max=n - 1)].to(torch.int16), torch.full_like(ia, -1, dtype=torch.int16))
+            tb = torch.where(ib < n, d.dT[torch.clamp(ib, max=n - 1)].to(torch.int16), torch.full_like(ib, -1, dtype=torch.int16))
+            diff = ta != tb
+            anyd = diff.any(dim=1)
+            first = torch.argmax(diff.to(torch.int8), dim=1)
+            va = ta.gather(1, first[:, None]).squeeze(1); vb = tb.gather(1, first[:, None]).squeeze(1)
+            bad = int((anyd & (va > vb)).sum())
+            undecided = int((~anyd).sum())
+        flags = torch.tensor([1 if perm_ok else 0, bad, undecided], dtype=torch.int64, device=dev)
+        mins = flags.clone(); dist.all_reduce(mins, op=dist.ReduceOp.MIN)
+        sums = flags.clone(); dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    ok = bool(mins[0].item() == 1 and sums[1].item() == 0)
+    return ok, {"permutation": bool(mins[0].item() == 1), "order_violations": int(sums[1].item()), "undecided_pairs": int(sums[2].item()),
+                "pairs_per_rank": pairs, "depth": depth}
+
+
 def distributed_suffix_array(ctx, dT, n):
     """Convenience wrapper: returns (sa_local, base, rounds)."""
     d = DistributedSA(ctx, dT, n)

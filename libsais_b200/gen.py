@@ -64,3 +64,30 @@ def repetitive_dna(base_len, copies, seed=3, rate_num=1049):
             code = np.where(hit, sub, base)
         out[c * base_len:(c + 1) * base_len] = _ACGT[code]
     return out
+
+
+def dna_torch(seed, n, device="cuda", chunk=1 << 27):
+    """Same iid ACGT text as dna(), generated on the device with torch integer ops (int64 wrap-around
+    arithmetic; logical shifts emulated with masks).  For texts too large to generate on the host in time."""
+    import torch
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+
+    def lsr(x, s):
+        return (x >> s) & ((1 << (64 - s)) - 1)
+
+    def c(v):                                     # 64-bit constant as a signed python int
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        i = torch.arange(lo, hi, dtype=torch.int64, device=device)
+        x = (seed << 40) + (i >> 5)
+        z = x + c(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        code = lsr(z, 1) >> ((i & 31) * 2 - 1).clamp(min=0)
+        code = torch.where((i & 31) == 0, z & 3, code & 3)
+        out[lo:hi] = lut[code]
+    return out

@@ -13,7 +13,7 @@ import torch.distributed as dist
 sys.path.insert(0, ".")
 import libsais_b200
 from libsais_b200 import gen
-from libsais_b200.dist import DistributedSA
+from libsais_b200.dist import DistributedSA, verify_distributed
 
 
 def main():
@@ -25,7 +25,10 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-    if kind == "dna":
+    dT = None
+    if kind == "dna" and n >= (1 << 27):
+        dT = gen.dna_torch(5, n, device="cuda")        # same text as gen.dna(5, n), generated on the device
+    elif kind == "dna":
         T = gen.dna(5, n)
     elif kind == "bytes":
         T = gen.rand_bytes(2, n)
@@ -35,10 +38,13 @@ def main():
         T = np.zeros(n, dtype=np.uint8)
     else:
         T = np.resize(np.frombuffer(b"abracadabra", dtype=np.uint8), n)
-    dT = torch.from_numpy(T).cuda()
+    if dT is None:
+        dT = torch.from_numpy(T).cuda()
     ctx = libsais_b200.Context(local)
-    d = DistributedSA(ctx, dT, n)
-    d.run()                                      # warm-up (workspace growth, NCCL channels)
+    if "--no-warmup" not in sys.argv:
+        d = DistributedSA(ctx, dT, n)
+        d.run()                                  # warm-up (workspace growth, NCCL channels)
+        del d
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
     d = DistributedSA(ctx, dT, n)
@@ -46,7 +52,11 @@ def main():
     torch.cuda.synchronize(); dist.barrier()
     dt = time.perf_counter() - t0
     ok = None
-    if verify:
+    vinfo = None
+    if "--verify-dist" in sys.argv:
+        okd, vinfo = verify_distributed(d)
+        vinfo["ok"] = okd
+    if verify and "--verify-dist" not in sys.argv:
         full = torch.empty(n, dtype=torch.int32, device="cuda")
         assert ctx.sa_dev(dT.data_ptr(), full.data_ptr(), n) == 0
         ok = bool(torch.equal(full[base: base + sa.numel()], sa))
@@ -59,7 +69,8 @@ def main():
     sizes = [None] * world
     dist.all_gather_object(sizes, int(sa.numel()))
     if rank == 0:
-        print(json.dumps({"n": n, "kind": kind, "world": world, "seconds": round(dt, 4), "mbs": round(n / 1e6 / dt, 1), "parity_vs_single_gpu": ok,
+        print(json.dumps({"n": n, "kind": kind, "world": world, "seconds": round(dt, 4), "mbs": round(n / 1e6 / dt, 1), "parity_vs_single_gpu": ok, "distributed_check": vinfo,
+                          "gpu_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
                           "slice_sizes": sizes, "rounds": [(r["h"], r["local"], r["active_local"]) for r in d.rounds]}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
