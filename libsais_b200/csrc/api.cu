@@ -655,6 +655,7 @@ int64_t libsais_cuda_scatter_u32_dev(const void *ctx, uint32_t *d_dst, int64_t d
     if (!c || !c->ok) return -2;
     if (count < 0 || dst_len < 0) return -1;
     Call call(*c);
+    c->reserve(scatter_workspace_bytes((u64)count) + 4096);      // best effort: without scratch the scatter is unpartitioned
     run_scatter_u32(*c, d_dst, (u64)dst_len, d_idx, d_val, (u64)count, idx_offset);
     return call.finish() ? 0 : -2;
 }

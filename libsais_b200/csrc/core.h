@@ -71,6 +71,7 @@ size_t sort_workspace_bytes(u64 count);
 int run_sort_pairs(Ctx &c, u64 *ka, u32 *va, u64 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit);
 int run_sort_u32_pairs(Ctx &c, u32 *ka, u32 *va, u32 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit);
 void run_gather_u32(Ctx &c, const u32 *src, u64 src_len, const u32 *idx, u64 count, u32 idx_offset, u32 *out);
+size_t scatter_workspace_bytes(u64 count);
 void run_scatter_u32(Ctx &c, u32 *dst, u64 dst_len, const u32 *idx, const u32 *val, u64 count, u32 idx_offset);
 
 // conversions used by the 64-bit API

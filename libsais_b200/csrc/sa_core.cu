@@ -766,16 +766,16 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
 // exchanges between them are NCCL all-to-alls issued from the host side.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-dist_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int k, int K, u64 lo, u64 count,
+dist_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int k, int K, int len_bits, u64 lo, u64 count,
                  u64 *__restrict__ keys, u32 *__restrict__ pos)
 {
     u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i >= count) return;
     u64 p = lo + i;
-    // the length field makes suffixes that run past the end unique and orders them before every
-    // longer suffix with the same zero-padded k-mer: no stability is asked of the distributed sort
-    u64 len = p + (u64)k <= n ? 127 : n - p;
-    keys[i] = (kmer_at(words, p, b, K) << 7) | len;
+    // the length field (all ones = full length) makes suffixes that run past the end unique and orders them
+    // before every longer suffix with the same zero-padded k-mer: no stability is asked of the distributed sort
+    u64 len = p + (u64)k <= n ? (((u64)1 << len_bits) - 1) : n - p;
+    keys[i] = (kmer_at(words, p, b, K) << len_bits) | len;
     pos[i] = (u32)p;
 }
 
@@ -794,7 +794,19 @@ int dist_prepare(Ctx &c, const u8 *d_T, u64 n, int *k_out, int *K_out)
         if (f) { ++sigma; double pr = (double)f / (double)n; entropy -= pr * std::log2(pr); }
     }
     const int b = bits_for((u64)(sigma > 1 ? sigma - 1 : 1));
-    const int k = choose_key_symbols(n, b, entropy, 56);
+    // <= 48 key bits + <= 6 length bits leave the top byte of the u64 free for the destination rank of the sample
+    // sort.  Unlike the single-GPU heuristic the key is NOT rounded up to whole digit passes: the length field
+    // shares the last digit.
+    int k;
+    {
+        int kmax = 48 / b; if (kmax < 1) kmax = 1;
+        double need = std::log2((double)(n < 2 ? 2 : n)) + 10.0;
+        double kk = std::ceil(need / (entropy < 0.05 ? 0.05 : entropy));
+        k = kk > (double)kmax ? kmax : (int)kk;
+        if (k < 1) k = 1;
+        const char *env = getenv("LIBSAIS_CUDA_KEY_SYMBOLS");
+        if (env && *env) { int kv = atoi(env); if (kv >= 1) k = kv < kmax ? kv : kmax; }
+    }
     const u64 nwords = ceil_div(n * (u64)b, 64) + 2;
     if (c.dist_words) { cudaFree(c.dist_words); c.dist_words = nullptr; }
     if (cudaMalloc(&c.dist_words, nwords * 8 + 256) != cudaSuccess) { cudaGetLastError(); return -2; }
@@ -810,7 +822,7 @@ int dist_keys(Ctx &c, u64 lo, u64 count, u64 *d_keys, u32 *d_pos)
 {
     if (!c.dist_words || lo + count > c.dist_n) return -1;
     if (count) LSC_LAUNCH(c, KC_MAKE_KEYS, (double)count * 13, dist_keys_kernel, (u32)ceil_div(count, 256), 256, 0,
-                          c.dist_words, c.dist_n, c.dist_b, c.dist_k, c.dist_k * c.dist_b, lo, count, d_keys, d_pos);
+                          c.dist_words, c.dist_n, c.dist_b, c.dist_k, c.dist_k * c.dist_b, bits_for((u64)c.dist_k), lo, count, d_keys, d_pos);
     return c.failed() ? -2 : 0;
 }
 
@@ -902,9 +914,33 @@ void run_gather_u32(Ctx &c, const u32 *src, u64 src_len, const u32 *idx, u64 cou
 {
     if (count) LSC_LAUNCH(c, KC_ROUND_KEYS, (double)count * 12, gather_u32_kernel, (u32)ceil_div(count, 256), 256, 0, src, src_len, idx, count, idx_offset, out);
 }
+size_t scatter_workspace_bytes(u64 count) { return (size_t)count * 8 + RadixSort<u32, u32>::temp_bytes(count) + 4096; }
+
+// dst[idx[i] - idx_offset] = val[i].  Large scatters go through the locality partition (scatter.cuh);
+// the partition digit is taken from idx itself, which is fine because idx - idx_offset preserves locality.
 void run_scatter_u32(Ctx &c, u32 *dst, u64 dst_len, const u32 *idx, const u32 *val, u64 count, u32 idx_offset)
 {
-    if (count) LSC_LAUNCH(c, KC_SCATTER, (double)count * 12, scatter_u32_kernel, (u32)ceil_div(count, 256), 256, 0, dst, dst_len, idx, val, count, idx_offset);
+    if (!count) return;
+    if (count >= (1ull << 20) && dst_len > (8ull << 20)) {
+        u32 *ib = c.alloc_n<u32>(count), *vb = c.alloc_n<u32>(count);
+        void *temp = c.alloc(RadixSort<u32, u32>::temp_bytes(count));
+        if (ib && vb && temp) {
+            u32 *err = (u32 *)(c.d_scalars + S_ERR);
+            c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, sizeof(u64), c.stream));
+            // one digit pass on the top 8 bits of the index range [idx_offset, idx_offset + dst_len)
+            const int bits = bits_for((u64)idx_offset + dst_len - 1);
+            const int lo = bits > kRadixBits ? bits - kRadixBits : 0;
+            c.pass_class_override = KC_SCATTER;
+            int where = RadixSort<u32, u32>::sort(c, const_cast<u32 *>(idx), const_cast<u32 *>(val), ib, vb, count, lo, bits, temp, err);
+            c.pass_class_override = -1;
+            if (where == 1) {
+                LSC_LAUNCH(c, KC_SCATTER, (double)count * 12, scatter_u32_kernel, (u32)ceil_div(count, 256), 256, 0, dst, dst_len, ib, vb, count, idx_offset);
+                return;
+            }
+        }
+        c.last_error = cudaSuccess;          // no scratch: fall through to the plain scatter
+    }
+    LSC_LAUNCH(c, KC_SCATTER, (double)count * 12, scatter_u32_kernel, (u32)ceil_div(count, 256), 256, 0, dst, dst_len, idx, val, count, idx_offset);
 }
 
 }  // namespace lsc

@@ -105,30 +105,27 @@ class DistributedSA:
                                                       keys.numel(), lo_bit, hi_bit), "sort_pairs")
         return (ka, va) if w == 1 else (keys, vals)
 
-    def _route(self, owner, payloads):
-        """Group items by destination rank `owner` (int32, values in [0, world]; world = drop) with the
-        library's stable partition pass; returns the permuted payloads and the per-destination counts."""
-        cnt = keys = None
+    def _route_pair(self, owner, a, b):
+        """Group (a, b) items (int32 tensors with u32 bit patterns) by destination rank `owner` (int64, values
+        in [0, world]; world = drop): destination and `a` share one u64 key, `b` rides as the value, so ONE
+        stable onesweep digit pass moves both.  Returns a, b in destination order and the per-destination counts."""
         nitems = owner.numel()
-        counts = torch.bincount(owner.long(), minlength=self.world + 1)[: self.world + 1].tolist()
-        outs = []
-        obits = _bits(self.world)
-        for p in payloads:
-            k = owner.clone()
-            v = p.clone()
-            ka, va = torch.empty_like(k), torch.empty_like(v)
-            w = _check(self.L.libsais_cuda_sort_u32_pairs_dev(self.h, k.data_ptr(), v.data_ptr(), ka.data_ptr(), va.data_ptr(),
-                                                              nitems, 0, obits), "route")
-            outs.append(va if w == 1 else v)
-        return outs, [int(c) for c in counts[: self.world]]
+        if nitems == 0:
+            return a, b, [0] * self.world
+        keys = (owner << 56) | _u32(a)
+        keys, b_s = self._sort_pairs(keys, b.clone(), 56, 56 + _bits(self.world))
+        probe = torch.arange(self.world + 1, dtype=torch.int64, device=owner.device)
+        edges = torch.searchsorted(keys >> 56, probe, right=False).tolist()
+        counts = [int(edges[i + 1] - edges[i]) for i in range(self.world)]
+        return (keys & _M32).to(torch.int32), b_s, counts
 
     def _owner_of(self, pos64):
-        return torch.clamp(pos64 // self.B, max=self.world - 1).to(torch.int32)
+        return torch.clamp(pos64 // self.B, max=self.world - 1)
 
     def _scatter_isa(self, pos, rank):
         """Route (position, rank) pairs to the owners of the positions and store them in the ISA slices."""
         owner = self._owner_of(_u32(pos))
-        (pos_s, rank_s), counts = self._route(owner, [pos, rank])
+        pos_s, rank_s, counts = self._route_pair(owner, pos, rank)
         pos_r, rc = _exchange(pos_s, counts, self.world)
         rank_r = _exchange_known(rank_s, counts, rc)
         if pos_r.numel():
@@ -145,38 +142,64 @@ class DistributedSA:
         torch.cuda.current_stream(self.dev).wait_stream(torch.cuda.ExternalStream(self.ctx.stream, device=self.dev))
         return out
 
+    def _tick(self, name):
+        if not self.timing:
+            return
+        import time
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        self.phases.append((name, round((t - self._t) * 1e3, 2)))
+        self._t = t
+
     def _run(self):
+        import os, time
+        self.timing = bool(os.environ.get("LSC_DIST_TIMING"))
+        self.phases = []
+        if self.timing:
+            torch.cuda.synchronize()
+        self._t = time.perf_counter()
         n, world, dev = self.n, self.world, self.dev
         k_out, kb_out = C.c_int32(0), C.c_int32(0)
         _check(self.L.libsais_cuda_dist_prepare(self.h, self.dT.data_ptr(), n, C.byref(k_out), C.byref(kb_out)), "dist_prepare")
         k, K = k_out.value, kb_out.value
-        key_bits = K + 7
+        self._tick("prepare_call")
+        key_bits = K + _bits(k)                 # k-mer + length field (see dist_keys_kernel)
         cnt = self.hi - self.lo
         self.isa = torch.zeros(max(cnt, 1), dtype=torch.int32, device=dev)
 
         # ---- round 0: keys of the owned positions, sample sort over the ranks
         keys = torch.empty(max(cnt, 1), dtype=torch.int64, device=dev)[:cnt]
         pos = torch.empty(max(cnt, 1), dtype=torch.int32, device=dev)[:cnt]
+        self._tick("alloc_round0")
         _check(self.L.libsais_cuda_dist_keys(self.h, self.lo, cnt, keys.data_ptr(), pos.data_ptr()), "dist_keys")
-        keys, pos = self._sort_pairs(keys, pos, 0, key_bits)
-        # splitters: regular samples of every rank's sorted keys (keys are < 2^63: signed order = unsigned order)
-        ns = min(self.samples, max(cnt, 1))
-        idx = (torch.arange(ns, device=dev, dtype=torch.int64) * max(cnt, 1)) // ns
-        mine = keys[idx] if cnt else torch.full((ns,), (1 << 62), dtype=torch.int64, device=dev)
-        if mine.numel() < self.samples:
-            mine = torch.cat([mine, mine[-1:].expand(self.samples - mine.numel())])
+        self._tick("keys")
+        # splitters from a random sample of the (unsorted) keys; keys are < 2^55: signed order = unsigned order
+        g = torch.Generator(device=dev); g.manual_seed(1234 + self.rank)
+        if cnt:
+            mine = keys[torch.randint(0, cnt, (self.samples,), device=dev, generator=g)]
+        else:
+            mine = torch.full((self.samples,), (1 << 62), dtype=torch.int64, device=dev)
         allsamp = torch.empty(self.samples * world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allsamp, mine.contiguous())
         allsamp, _ = torch.sort(allsamp)                                  # 8192*G values: plumbing, not the data path
         splitters = allsamp[[(i * allsamp.numel()) // world for i in range(1, world)]] if world > 1 else allsamp[:0]
-        # destination of a key = number of splitters <= key: equal keys share a destination
-        bounds = torch.searchsorted(keys, splitters, right=False) if world > 1 else keys.new_zeros(0)
-        edges = [0] + [int(x) for x in bounds.tolist()] + [cnt]
-        counts = [edges[i + 1] - edges[i] for i in range(world)]
+        # destination of a key = number of splitters <= key (equal keys share a destination); it rides in the
+        # key's free top byte, so ONE onesweep digit pass groups the (key, position) pairs by destination
+        if world > 1:
+            dest = torch.bucketize(keys, splitters, right=True)
+            keys |= dest << 56
+            keys, pos = self._sort_pairs(keys, pos, 56, 56 + _bits(world - 1))
+            edges = torch.searchsorted(keys >> 56, torch.arange(world + 1, device=dev, dtype=torch.int64), right=False).tolist()
+        else:
+            edges = [0, cnt]
+        counts = [int(edges[i + 1] - edges[i]) for i in range(world)]
+        self._tick("splitters")
         keys_r, rc = _exchange(keys, counts, world)
         pos_r = _exchange_known(pos, counts, rc)
+        self._tick("all_to_all_keys")
         m = keys_r.numel()
         keys_r, pos_r = self._sort_pairs(keys_r, pos_r, 0, key_bits)      # merge of the received sorted runs
+        self._tick("merge_sort")
         sizes = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sizes, torch.tensor([m], dtype=torch.int64, device=dev))
         sizes = sizes.tolist()
@@ -184,6 +207,7 @@ class DistributedSA:
         self.sa_local = torch.empty(max(m, 1), dtype=torch.int32, device=dev)[:m]
 
         act_pos, act_slot, act_grp, n_act, n_grp = self._rank_stage(keys_r, pos_r, None, m)
+        self._tick("rank_stage0+isa")
         del keys_r, pos_r, keys, pos
         self.rounds.append({"h": 0, "local": m, "active_local": n_act})
 
@@ -198,9 +222,9 @@ class DistributedSA:
             # k2 = ISA[p + h] + 1 (0 past the end): request / response all-to-all with the position owners
             q = _u32(act_pos) + h
             valid = q < n
-            owner = torch.where(valid, torch.clamp(q // self.B, max=world - 1), torch.full_like(q, world)).to(torch.int32)
+            owner = torch.where(valid, torch.clamp(q // self.B, max=world - 1), torch.full_like(q, world))
             ident = torch.arange(n_act, dtype=torch.int32, device=dev)
-            (q_s, id_s), counts = self._route(owner, [q.to(torch.int32), ident])
+            q_s, id_s, counts = self._route_pair(owner, q.to(torch.int32), ident)
             nreq = sum(counts)
             req, rc = _exchange(q_s[:nreq].contiguous(), counts, world)
             ans = torch.empty(max(req.numel(), 1), dtype=torch.int32, device=dev)[: req.numel()]
@@ -217,6 +241,7 @@ class DistributedSA:
             act_pos, act_slot, act_grp, n_act_new, n_grp = self._rank_stage(keys, spos, act_slot, n_act)
             self.rounds.append({"h": h, "local": n_act, "active_local": n_act_new})
             n_act = n_act_new
+            self._tick("round_h%d" % h)
             h *= 2
             if len(self.rounds) > 80:
                 raise RuntimeError("distributed prefix doubling did not converge")
@@ -248,7 +273,7 @@ def verify_distributed(d, pairs=200000, depth=256, seed=1):
     with torch.cuda.stream(torch.cuda.ExternalStream(d.ctx.stream, device=dev)):
         sa = d.sa_local
         owner = d._owner_of(_u32(sa))
-        (pos_s,), counts = d._route(owner, [sa])
+        pos_s, _unused, counts = d._route_pair(owner, sa, sa)
         got, _ = _exchange(pos_s, counts, world)
         cnt = d.hi - d.lo
         seen = torch.zeros(max(cnt, 1), dtype=torch.int32, device=dev)

@@ -70,7 +70,7 @@ def main():
     dist.all_gather_object(sizes, int(sa.numel()))
     if rank == 0:
         print(json.dumps({"n": n, "kind": kind, "world": world, "seconds": round(dt, 4), "mbs": round(n / 1e6 / dt, 1), "parity_vs_single_gpu": ok, "distributed_check": vinfo,
-                          "gpu_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
+                          "gpu_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1), "phases_ms_rank0": getattr(d, "phases", None) or None,
                           "slice_sizes": sizes, "rounds": [(r["h"], r["local"], r["active_local"]) for r in d.rounds]}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
