@@ -319,6 +319,10 @@ def main():
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                     "algorithmic_bytes_per_launch": dom["bytes"] / max(dom["launches"], 1),
                     "avg_launch_ms": dom["ms"] / max(dom["launches"], 1), "launches": dom["launches"],
+                    "note": "achieved = sum of algorithmic bytes / sum of CUDA-event time over ALL launches of the kernel in the timed "
+                            "region (4 full-size passes of 2*n*12 B + 6 small passes of the ~64K unresolved suffixes per step); "
+                            "traffic = dram read+write bytes of ONE full-size launch (ncu), to compare with full_size_algorithmic_bytes",
+                    "full_size_algorithmic_bytes": 2 * n * 12,
                     "share_of_step": round(dom["ms"] / dev_ms, 4)}
         kern = {k: {"launches": v["launches"], "ms_per_step": round(v["ms"] / args.steps, 4),
                     "algo_gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in agg.items()}
