@@ -94,6 +94,14 @@ int64_t libsais_cuda_sort_u32_pairs_dev(const void * ctx, uint32_t * d_keys, uin
 int64_t libsais_cuda_rank_stage_dev(const void * ctx, const uint64_t * d_keys, const uint32_t * d_pos, const uint32_t * d_slot_in,
                                     int64_t count, uint32_t slot_base, uint32_t * d_sa_local, uint32_t * d_pair_pos, uint32_t * d_pair_rank,
                                     uint32_t * d_act_pos, uint32_t * d_act_slot, uint32_t * d_act_grp, uint64_t * counts_out);
+/* Routing for the all-to-alls.  route: items (a[i], b[i]) are grouped by destination rank min(world-1, (a[i]+add)/block)
+ * (items with a[i]+add >= limit are dropped behind the last rank) with one onesweep digit pass; outputs hold a[i]+add and
+ * b[i] in destination order, counts_out[0..world) the items per destination.  partition: round-0 sample sort, destination
+ * = number of splitters <= key (kept in the key's top byte), counts_out[0..nsplit]. */
+int64_t libsais_cuda_dist_route_dev(const void * ctx, const uint32_t * d_a, const uint32_t * d_b, int64_t count, int64_t add, int64_t limit,
+                                    int64_t block, int32_t world, uint32_t * d_a_out, uint32_t * d_b_out, uint64_t * counts_out);
+int64_t libsais_cuda_dist_partition_dev(const void * ctx, uint64_t * d_keys, uint32_t * d_pos, int64_t count, const uint64_t * d_splitters,
+                                        int32_t nsplit, uint64_t * d_keys_out, uint32_t * d_pos_out, uint64_t * counts_out);
 /* out[i] = src[idx[i] - idx_offset] (0 when out of range);  dst[idx[i] - idx_offset] = val[i]. */
 int64_t libsais_cuda_gather_u32_dev(const void * ctx, const uint32_t * d_src, int64_t src_len, const uint32_t * d_idx, int64_t count,
                                     uint32_t idx_offset, uint32_t * d_out);

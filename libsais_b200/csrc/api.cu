@@ -660,4 +660,31 @@ int64_t libsais_cuda_scatter_u32_dev(const void *ctx, uint32_t *d_dst, int64_t d
     return call.finish() ? 0 : -2;
 }
 
+int64_t libsais_cuda_dist_route_dev(const void *ctx, const uint32_t *d_a, const uint32_t *d_b, int64_t count, int64_t add, int64_t limit,
+                                    int64_t block, int32_t world, uint32_t *d_a_out, uint32_t *d_b_out, uint64_t *counts_out)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (count < 0 || add < 0 || limit < 0 || block <= 0 || world <= 0 || counts_out == nullptr) return -1;
+    Call call(*c);
+    if (!c->reserve(route_workspace_bytes((u64)count) + 4096)) return -2;
+    u64 counts[64] = {0};
+    int rc = run_route(*c, d_a, d_b, (u64)count, (u64)add, (u64)limit, (u64)block, (u32)world, d_a_out, d_b_out, counts);
+    for (int r = 0; r < world && r < 64; ++r) counts_out[r] = counts[r];
+    return rc == 0 && call.finish() ? 0 : (rc == -1 ? -1 : -2);
+}
+int64_t libsais_cuda_dist_partition_dev(const void *ctx, uint64_t *d_keys, uint32_t *d_pos, int64_t count, const uint64_t *d_splitters,
+                                        int32_t nsplit, uint64_t *d_keys_out, uint32_t *d_pos_out, uint64_t *counts_out)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c || !c->ok) return -2;
+    if (count < 0 || nsplit < 0 || counts_out == nullptr) return -1;
+    Call call(*c);
+    if (!c->reserve(sort_workspace_bytes((u64)count) + 4096)) return -2;
+    u64 counts[65] = {0};
+    int rc = run_partition_by_splitters(*c, d_keys, d_pos, (u64)count, d_splitters, (u32)nsplit, d_keys_out, d_pos_out, counts);
+    for (int r = 0; r <= nsplit && r < 65; ++r) counts_out[r] = counts[r];
+    return rc == 0 && call.finish() ? 0 : (rc == -1 ? -1 : -2);
+}
+
 }  // extern "C"

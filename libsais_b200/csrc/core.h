@@ -16,6 +16,7 @@ enum ScalarSlot {
     S_MISC    = 272,   // [272, 304): LUT staging; [312, 320): debug counters
     S_GSA_TOTAL = 320, // number of separators of a GSA text
     S_GSA_INVALID = 321, // set when the collection has an empty member (reference returns -1)
+    S_ROUTE   = 384,   // [384, 449): per-destination counts of the distributed routing
     S_SGRAM   = 512    // [512, 768): s-gram histogram of the text
 };
 
@@ -71,6 +72,11 @@ size_t sort_workspace_bytes(u64 count);
 int run_sort_pairs(Ctx &c, u64 *ka, u32 *va, u64 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit);
 int run_sort_u32_pairs(Ctx &c, u32 *ka, u32 *va, u32 *kb, u32 *vb, u64 count, int lo_bit, int hi_bit);
 void run_gather_u32(Ctx &c, const u32 *src, u64 src_len, const u32 *idx, u64 count, u32 idx_offset, u32 *out);
+size_t route_workspace_bytes(u64 count);
+int run_route(Ctx &c, const u32 *d_a, const u32 *d_b, u64 count, u64 add, u64 limit, u64 block, u32 world,
+              u32 *d_a_out, u32 *d_b_out, u64 *counts_out);
+int run_partition_by_splitters(Ctx &c, u64 *d_keys, u32 *d_pos, u64 count, const u64 *d_splitters, u32 nsplit,
+                               u64 *d_keys_out, u32 *d_pos_out, u64 *counts_out);
 size_t scatter_workspace_bytes(u64 count);
 void run_scatter_u32(Ctx &c, u32 *dst, u64 dst_len, const u32 *idx, const u32 *val, u64 count, u32 idx_offset);
 

@@ -943,4 +943,119 @@ void run_scatter_u32(Ctx &c, u32 *dst, u64 dst_len, const u32 *idx, const u32 *v
     LSC_LAUNCH(c, KC_SCATTER, (double)count * 12, scatter_u32_kernel, (u32)ceil_div(count, 256), 256, 0, dst, dst_len, idx, val, count, idx_offset);
 }
 
+
+// ---- routing for the all-to-alls: items are grouped by destination rank with ONE onesweep digit pass.
+// The destination rides in bits [56, 64) of a u64 key whose low 32 bits carry the first payload word.
+static const int kRouteMaxRanks = 64;
+
+__global__ void __launch_bounds__(256)
+route_pack_kernel(const u32 *__restrict__ a, u64 count, u64 add, u64 limit, u64 block, u32 world,
+                  u64 *__restrict__ keys, u64 *__restrict__ dest_counts)
+{
+    __shared__ u32 sh[kRouteMaxRanks + 1];
+    if (threadIdx.x <= kRouteMaxRanks) sh[threadIdx.x] = 0;
+    __syncthreads();
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < count) {
+        u64 v = (u64)a[i] + add;                              // position (add = 0) or requested position p + h
+        u64 owner = v < limit ? v / block : (u64)world;       // beyond the text: dropped (sorted behind every rank)
+        if (owner > (u64)world) owner = world;
+        if (v < limit && owner >= world) owner = world - 1;
+        keys[i] = (owner << 56) | (v & 0xFFFFFFFFull);
+        atomicAdd(&sh[owner], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x <= world && sh[threadIdx.x]) atomicAdd((unsigned long long *)&dest_counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+route_unpack_kernel(const u64 *__restrict__ keys, u64 count, u32 *__restrict__ a_out)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < count) a_out[i] = (u32)keys[i];
+}
+
+// keys |= (number of splitters <= key) << 56, per-destination counts
+__global__ void __launch_bounds__(256)
+splitter_dest_kernel(u64 *__restrict__ keys, u64 count, const u64 *__restrict__ splitters, u32 nsplit, u64 *__restrict__ dest_counts)
+{
+    __shared__ u32 sh[kRouteMaxRanks + 1];
+    __shared__ u64 sp[kRouteMaxRanks];
+    if (threadIdx.x <= kRouteMaxRanks) sh[threadIdx.x] = 0;
+    if (threadIdx.x < nsplit) sp[threadIdx.x] = splitters[threadIdx.x];
+    __syncthreads();
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < count) {
+        u64 k = keys[i];
+        u32 d = 0;
+        for (u32 j = 0; j < nsplit; ++j) d += sp[j] <= k ? 1u : 0u;
+        keys[i] = k | ((u64)d << 56);
+        atomicAdd(&sh[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x <= nsplit && sh[threadIdx.x]) atomicAdd((unsigned long long *)&dest_counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+size_t route_workspace_bytes(u64 count) { return (size_t)count * (8 + 8 + 4) + RadixSort<u64, u32>::temp_bytes(count) + 8192; }
+
+// Group (a, b) items by owner((a + add) / block): outputs in destination order, counts_out[0..world) on the host.
+int run_route(Ctx &c, const u32 *d_a, const u32 *d_b, u64 count, u64 add, u64 limit, u64 block, u32 world,
+              u32 *d_a_out, u32 *d_b_out, u64 *counts_out)
+{
+    for (u32 r = 0; r < world; ++r) counts_out[r] = 0;
+    if (world == 0 || world > kRouteMaxRanks) return -1;
+    if (count == 0) return 0;
+    u64 *keyA = c.alloc_n<u64>(count), *keyB = c.alloc_n<u64>(count);
+    u32 *valA = c.alloc_n<u32>(count);
+    void *temp = c.alloc(RadixSort<u64, u32>::temp_bytes(count));
+    if (!keyA || !keyB || !valA || !temp) return -2;
+    u64 *dcnt = c.d_scalars + S_ROUTE;
+    u32 *err = (u32 *)(c.d_scalars + S_ERR);
+    c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, sizeof(u64), c.stream));
+    c.check(cudaMemsetAsync(dcnt, 0, (kRouteMaxRanks + 1) * sizeof(u64), c.stream));
+    c.check(cudaMemcpyAsync(valA, d_b, count * 4, cudaMemcpyDeviceToDevice, c.stream));
+    LSC_LAUNCH(c, KC_SCATTER, (double)count * 12, route_pack_kernel, (u32)ceil_div(count, 256), 256, 0, d_a, count, add, limit, block, world, keyA, dcnt);
+    c.pass_class_override = KC_SCATTER;
+    int where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, d_b_out, count, 56, 56 + bits_for(world), temp, err);
+    c.pass_class_override = -1;
+    if (where != 1) return -2;
+    LSC_LAUNCH(c, KC_SCATTER, (double)count * 12, route_unpack_kernel, (u32)ceil_div(count, 256), 256, 0, keyB, count, d_a_out);
+    c.check(cudaMemcpyAsync(c.h_scalars + S_ROUTE, dcnt, (kRouteMaxRanks + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c.stream));
+    if (!c.sync() || c.failed()) return -2;
+    for (u32 r = 0; r < world; ++r) counts_out[r] = c.h_scalars[S_ROUTE + r];
+    return 0;
+}
+
+// Round-0 sample sort: destination = number of splitters <= key; one digit pass groups (key, pos) by destination.
+// Result in (d_keys_out, d_pos_out); the keys keep the destination in their top byte.
+int run_partition_by_splitters(Ctx &c, u64 *d_keys, u32 *d_pos, u64 count, const u64 *d_splitters, u32 nsplit,
+                               u64 *d_keys_out, u32 *d_pos_out, u64 *counts_out)
+{
+    for (u32 r = 0; r <= nsplit; ++r) counts_out[r] = 0;
+    if (nsplit >= kRouteMaxRanks) return -1;
+    if (count == 0) return 0;
+    void *temp = c.alloc(RadixSort<u64, u32>::temp_bytes(count));
+    if (!temp) return -2;
+    u64 *dcnt = c.d_scalars + S_ROUTE;
+    u32 *err = (u32 *)(c.d_scalars + S_ERR);
+    c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, sizeof(u64), c.stream));
+    c.check(cudaMemsetAsync(dcnt, 0, (kRouteMaxRanks + 1) * sizeof(u64), c.stream));
+    LSC_LAUNCH(c, KC_SCATTER, (double)count * 16, splitter_dest_kernel, (u32)ceil_div(count, 256), 256, 0, d_keys, count, d_splitters, nsplit, dcnt);
+    int where;
+    if (nsplit == 0) {
+        c.check(cudaMemcpyAsync(d_keys_out, d_keys, count * 8, cudaMemcpyDeviceToDevice, c.stream));
+        c.check(cudaMemcpyAsync(d_pos_out, d_pos, count * 4, cudaMemcpyDeviceToDevice, c.stream));
+        where = 1;
+    } else {
+        c.pass_class_override = KC_SCATTER;
+        where = RadixSort<u64, u32>::sort(c, d_keys, d_pos, d_keys_out, d_pos_out, count, 56, 56 + bits_for(nsplit), temp, err);
+        c.pass_class_override = -1;
+    }
+    if (where != 1) return -2;
+    c.check(cudaMemcpyAsync(c.h_scalars + S_ROUTE, dcnt, (kRouteMaxRanks + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c.stream));
+    if (!c.sync() || c.failed()) return -2;
+    for (u32 r = 0; r <= nsplit; ++r) counts_out[r] = c.h_scalars[S_ROUTE + r];
+    return 0;
+}
+
 }  // namespace lsc

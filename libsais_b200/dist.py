@@ -55,6 +55,10 @@ class _Lib:
         lib.libsais_cuda_gather_u32_dev.argtypes = [vp, vp, i64, vp, i64, u32, vp]
         lib.libsais_cuda_scatter_u32_dev.restype = i64
         lib.libsais_cuda_scatter_u32_dev.argtypes = [vp, vp, i64, vp, vp, i64, u32]
+        lib.libsais_cuda_dist_route_dev.restype = i64
+        lib.libsais_cuda_dist_route_dev.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, vp, vp, C.POINTER(C.c_uint64)]
+        lib.libsais_cuda_dist_partition_dev.restype = i64
+        lib.libsais_cuda_dist_partition_dev.argtypes = [vp, vp, vp, i64, vp, i32, vp, vp, C.POINTER(C.c_uint64)]
         self.lib = lib
 
 
@@ -105,27 +109,23 @@ class DistributedSA:
                                                       keys.numel(), lo_bit, hi_bit), "sort_pairs")
         return (ka, va) if w == 1 else (keys, vals)
 
-    def _route_pair(self, owner, a, b):
-        """Group (a, b) items (int32 tensors with u32 bit patterns) by destination rank `owner` (int64, values
-        in [0, world]; world = drop): destination and `a` share one u64 key, `b` rides as the value, so ONE
-        stable onesweep digit pass moves both.  Returns a, b in destination order and the per-destination counts."""
-        nitems = owner.numel()
-        if nitems == 0:
-            return a, b, [0] * self.world
-        keys = (owner << 56) | _u32(a)
-        keys, b_s = self._sort_pairs(keys, b.clone(), 56, 56 + _bits(self.world))
-        probe = torch.arange(self.world + 1, dtype=torch.int64, device=owner.device)
-        edges = torch.searchsorted(keys >> 56, probe, right=False).tolist()
-        counts = [int(edges[i + 1] - edges[i]) for i in range(self.world)]
-        return (keys & _M32).to(torch.int32), b_s, counts
-
-    def _owner_of(self, pos64):
-        return torch.clamp(pos64 // self.B, max=self.world - 1)
+    def _route(self, a, b, add=0):
+        """Group (a, b) items (int32 tensors, u32 bit patterns) by the owner of position a + add with the library's
+        routing kernels (one onesweep digit pass); items with a + add >= n are dropped.  Returns a + add and b in
+        destination order (only the routed items) and the per-destination counts."""
+        nitems = a.numel()
+        a_out = torch.empty(max(nitems, 1), dtype=torch.int32, device=self.dev)
+        b_out = torch.empty(max(nitems, 1), dtype=torch.int32, device=self.dev)
+        counts = (C.c_uint64 * 64)()
+        _check(self.L.libsais_cuda_dist_route_dev(self.h, a.data_ptr(), b.data_ptr(), nitems, add, self.n, self.B, self.world,
+                                                  a_out.data_ptr(), b_out.data_ptr(), counts), "route")
+        counts = [int(counts[i]) for i in range(self.world)]
+        tot = sum(counts)
+        return a_out[:tot], b_out[:tot], counts
 
     def _scatter_isa(self, pos, rank):
         """Route (position, rank) pairs to the owners of the positions and store them in the ISA slices."""
-        owner = self._owner_of(_u32(pos))
-        pos_s, rank_s, counts = self._route_pair(owner, pos, rank)
+        pos_s, rank_s, counts = self._route(pos, rank)
         pos_r, rc = _exchange(pos_s, counts, self.world)
         rank_r = _exchange_known(rank_s, counts, rc)
         if pos_r.numel():
@@ -185,14 +185,12 @@ class DistributedSA:
         splitters = allsamp[[(i * allsamp.numel()) // world for i in range(1, world)]] if world > 1 else allsamp[:0]
         # destination of a key = number of splitters <= key (equal keys share a destination); it rides in the
         # key's free top byte, so ONE onesweep digit pass groups the (key, position) pairs by destination
-        if world > 1:
-            dest = torch.bucketize(keys, splitters, right=True)
-            keys |= dest << 56
-            keys, pos = self._sort_pairs(keys, pos, 56, 56 + _bits(world - 1))
-            edges = torch.searchsorted(keys >> 56, torch.arange(world + 1, device=dev, dtype=torch.int64), right=False).tolist()
-        else:
-            edges = [0, cnt]
-        counts = [int(edges[i + 1] - edges[i]) for i in range(world)]
+        keys_p, pos_p = torch.empty_like(keys), torch.empty_like(pos)
+        cbuf = (C.c_uint64 * 65)()
+        _check(self.L.libsais_cuda_dist_partition_dev(self.h, keys.data_ptr(), pos.data_ptr(), cnt, splitters.contiguous().data_ptr(), world - 1,
+                                                      keys_p.data_ptr(), pos_p.data_ptr(), cbuf), "partition")
+        keys, pos = keys_p, pos_p
+        counts = [int(cbuf[i]) for i in range(world)]
         self._tick("splitters")
         keys_r, rc = _exchange(keys, counts, world)
         pos_r = _exchange_known(pos, counts, rc)
@@ -220,13 +218,10 @@ class DistributedSA:
             if int(tot.item()) == 0:
                 break
             # k2 = ISA[p + h] + 1 (0 past the end): request / response all-to-all with the position owners
-            q = _u32(act_pos) + h
-            valid = q < n
-            owner = torch.where(valid, torch.clamp(q // self.B, max=world - 1), torch.full_like(q, world))
             ident = torch.arange(n_act, dtype=torch.int32, device=dev)
-            q_s, id_s, counts = self._route_pair(owner, q.to(torch.int32), ident)
+            q_s, id_s, counts = self._route(act_pos, ident, add=h)
             nreq = sum(counts)
-            req, rc = _exchange(q_s[:nreq].contiguous(), counts, world)
+            req, rc = _exchange(q_s, counts, world)
             ans = torch.empty(max(req.numel(), 1), dtype=torch.int32, device=dev)[: req.numel()]
             if req.numel():
                 _check(self.L.libsais_cuda_gather_u32_dev(self.h, self.isa.data_ptr(), self.isa.numel(), req.data_ptr(), req.numel(),
@@ -234,7 +229,7 @@ class DistributedSA:
             resp = _exchange_known(ans, rc, counts)
             k2 = torch.zeros(max(n_act, 1), dtype=torch.int64, device=dev)[:n_act]
             if nreq:
-                k2[id_s[:nreq].long()] = _u32(resp) + 1
+                k2[id_s.long()] = _u32(resp) + 1
             grp_bits = _bits(max(n_grp - 1, 1))
             keys = (_u32(act_grp) << rank_bits) | k2
             keys, spos = self._sort_pairs(keys, act_pos.clone(), 0, rank_bits + grp_bits)
@@ -272,8 +267,7 @@ def verify_distributed(d, pairs=200000, depth=256, seed=1):
     dev, n, world = d.dev, d.n, d.world
     with torch.cuda.stream(torch.cuda.ExternalStream(d.ctx.stream, device=dev)):
         sa = d.sa_local
-        owner = d._owner_of(_u32(sa))
-        pos_s, _unused, counts = d._route_pair(owner, sa, sa)
+        pos_s, _unused, counts = d._route(sa, sa)
         got, _ = _exchange(pos_s, counts, world)
         cnt = d.hi - d.lo
         seen = torch.zeros(max(cnt, 1), dtype=torch.int32, device=dev)
