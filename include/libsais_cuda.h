@@ -53,6 +53,8 @@ int32_t libsais_cuda_set_profiling(const void * ctx, int32_t on);
 int32_t libsais_cuda_get_stats(const void * ctx, libsais_cuda_stats * out);
 int32_t libsais_cuda_get_round(const void * ctx, int32_t round, libsais_cuda_round * out);
 const char * libsais_cuda_kernel_class_name(int32_t kernel_class);
+/* Contexts keep their (grow-only) device workspace between calls; this returns it to the system. */
+int32_t libsais_cuda_release_workspace(const void * ctx);
 /* Debug aid: raw internal device counters (look-back statistics in -DLSC_LOOKBACK_STATS builds). */
 int32_t libsais_cuda_debug_scalars(const void * ctx, uint32_t * out, int32_t count);
 /* cudaError_t of the last failure seen by the context (0 = none). */

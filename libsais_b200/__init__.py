@@ -59,9 +59,8 @@ def load_library(build_if_missing=True):
     lib.libsais_cuda_kernel_class_name.restype = C.c_char_p
     lib.libsais_cuda_kernel_class_name.argtypes = [i32]
     lib.libsais_cuda_last_error.argtypes = [vp]
-    for name, nargs in (("sa_dev", 4), ("bwt_dev", 4), ("plcp_dev", 5), ("lcp_dev", 5), ("unbwt_dev", 5)):
-        fn = getattr(lib, "libsais_cuda_" + name)
-        fn.restype = i64
+    for name in ("sa_dev", "bwt_dev", "plcp_dev", "lcp_dev", "unbwt_dev"):
+        getattr(lib, "libsais_cuda_" + name).restype = i64
     lib.libsais_cuda_sa_dev.argtypes = [vp, vp, vp, i64]
     lib.libsais_cuda_bwt_dev.argtypes = [vp, vp, vp, i64]
     lib.libsais_cuda_plcp_dev.argtypes = [vp, vp, vp, vp, i64]

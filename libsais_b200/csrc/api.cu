@@ -478,6 +478,19 @@ int32_t libsais_cuda_get_round(const void *ctx, int32_t round, libsais_cuda_roun
     out->h = r.h; out->n_active = r.n_active; out->n_groups = r.n_groups; out->passes = r.passes; out->key_bits = r.key_bits;
     return 0;
 }
+// Give the context's device workspace and pinned staging back to the system (it is re-grown on the next call).
+int32_t libsais_cuda_release_workspace(const void *ctx)
+{
+    Ctx *c = ctx ? as_ctx(ctx) : default_ctx();
+    if (!c) return -1;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->ws) { cudaFree(c->ws); c->ws = nullptr; c->ws_cap = 0; c->ws_off = 0; }
+    if (c->dist_words) { cudaFree(c->dist_words); c->dist_words = nullptr; }
+    c->free_staging();
+    cudaGetLastError();
+    return 0;
+}
 const char *libsais_cuda_kernel_class_name(int32_t kc) { return kc >= 0 && kc < KC_COUNT ? kKernelClassName[kc] : ""; }
 // debug: raw device scalars S_ERR.. (look-back statistics when built with -DLSC_LOOKBACK_STATS)
 int32_t libsais_cuda_debug_scalars(const void *ctx, uint32_t *out, int32_t count)
