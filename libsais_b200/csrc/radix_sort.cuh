@@ -1,11 +1,12 @@
 // radix_sort.cuh -- hand-written onesweep LSD radix sort for (key, value) pairs on sm_100a.
 //
-// One upfront kernel builds the histograms of every digit; each digit pass is then ONE kernel
-// that reads the tile once and writes it once ("onesweep"): warp-level multisplit with
-// match.any, a chained scan over tiles with decoupled look-back per digit, staging of the
-// tile in shared memory so the scatter leaves the SM as runs of consecutive addresses.
-// Stable; tiles are claimed through an atomic ticket so a tile's predecessors are always
-// resident (forward progress of the look-back).
+// One upfront kernel builds the histograms of every digit (or the caller supplies them); each
+// digit pass is then ONE kernel that reads the tile once and writes it once ("onesweep"): TMA
+// bulk loads of the tile, warp-level multisplit with ballots, a chained scan over tiles with
+// decoupled look-back per digit, staging of the tile in shared memory so the scatter leaves
+// the SM as runs of consecutive addresses.  Stable; tiles are claimed through an atomic ticket
+// so a tile's predecessors are always resident (forward progress of the look-back); a spin
+// watchdog turns a would-be hang into an error code.
 //
 // Replaces, as the ordering engine of the SA core, the reference's induced-sorting scans
 // (reference src/libsais.c:2157-4101 and :4777-6265); see DESIGN.md §3.

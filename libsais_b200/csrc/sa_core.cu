@@ -6,11 +6,16 @@
 // Pipeline:
 //   hist_sym      byte histogram (freq[], alphabet map)                      [~ :1398-1427]
 //   pack          symbols -> order-preserving b-bit codes, big-endian bitstream
-//   make_keys     key(p) = first k codes of suffix p (K = k*b <= 64 bits), in DESCENDING p
+//   round 0       key(p) = first k codes of suffix p (K = k*b <= 64 bits), elements in DESCENDING p.
+//                 The key array is never materialised: KmerGen feeds the first onesweep pass, and the
+//                 digit histograms of all passes come from the text's s-gram / byte histogram.
 //   onesweep      stable LSD radix sort of (key, p)                          radix_sort.cuh
-//   rank<ROUND0>  head flags, rank = slot of group head, SA/ISA scatter, compaction of the
-//                 suffixes whose group is not yet a singleton ("active")
-//   repeat while active: round_keys (g, ISA[p+h]+1) -> onesweep -> rank<false>; h doubles
+//   rank stage    rank_flags -> rank_scan -> rank_apply: head flags, rank = slot of the group head,
+//                 SA / BWT rows / primary / aux outputs, compaction of the suffixes whose group is
+//                 not yet a singleton ("active"); ranks reach ISA through the locality-partitioned
+//                 scatter (scatter.cuh) -- or not at all when few suffixes stay active (lazy ISA)
+//   repeat while active: round_keys (g, ISA[p+h]+1) -> onesweep -> rank stage; h doubles
+//   (bottom of the file: building blocks of the distributed variant, libsais_b200/dist.py)
 //
 // End-of-text rule ("a suffix that is a prefix of another sorts first", reference
 // include/libsais.h:76-84): keys are zero padded, the initial sort is stable over elements
