@@ -67,6 +67,23 @@ struct NoGen {
     __device__ __forceinline__ u32 val(u64) const { return 0; }
 };
 
+// One warp adds its 32 digits to a shared-memory histogram.  Sorted or skewed inputs put long runs of
+// one digit into a warp (32 serialised adds to one address); each run is added once, by its first
+// lane, with the run length.  Warp-collective: every lane calls it, `valid` masks lanes out.
+__device__ __forceinline__ void warp_hist_add(u32 *bins, u32 d, bool valid, int lane)
+{
+    const u32 dp = __shfl_up_sync(0xffffffffu, d, 1);
+    const u32 vm = __ballot_sync(0xffffffffu, valid);
+    const bool head = valid && (lane == 0 || !((vm >> (lane - 1)) & 1u) || dp != d);
+    const u32 hm = __ballot_sync(0xffffffffu, head);
+    if (head) {
+        const u32 above = ~((2u << lane) - 1u);            // lanes above mine (0 for lane 31)
+        const u32 stop = (hm | ~vm) & above;               // next run head, or first masked-out lane
+        const int end = stop ? __ffs(stop) - 1 : 32;
+        atomicAdd(&bins[d], (u32)(end - lane));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Upfront histograms of all digits: hist[pass][256] (u64).  One read of the keys.
 // ---------------------------------------------------------------------------------------------
@@ -75,7 +92,7 @@ __global__ void __launch_bounds__(THREADS)
 sort_hist_kernel(const KeyT *__restrict__ keys, u64 n, SortPlan plan, u64 *__restrict__ hist, const Gen gen)
 {
     __shared__ u32 sh[kMaxPasses * kRadixSize];
-    const int P = plan.passes;
+    const int P = plan.passes, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < P * kRadixSize; i += THREADS) sh[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * THREADS;
@@ -84,16 +101,8 @@ sort_hist_kernel(const KeyT *__restrict__ keys, u64 n, SortPlan plan, u64 *__res
         u64 idx = r * stride + (u64)blockIdx.x * THREADS + threadIdx.x;
         bool valid = idx < n;
         KeyT k = valid ? (Gen::kActive ? (KeyT)gen.key(idx) : keys[idx]) : (KeyT)0;
-        for (int p = 0; p < P; ++p) {
-            u32 d = digit_of(k, plan.shift[p], (1u << plan.nbits[p]) - 1);
-            u32 d0 = __shfl_sync(0xffffffffu, d, 0);
-            // skew fast path: a warp whose keys all share the digit issues one add, not 32 serialised ones
-            if (__all_sync(0xffffffffu, valid && d == d0)) {
-                if ((threadIdx.x & 31) == 0) atomicAdd(&sh[p * kRadixSize + d0], 32u);
-            } else if (valid) {
-                atomicAdd(&sh[p * kRadixSize + d], 1u);
-            }
-        }
+        for (int p = 0; p < P; ++p)
+            warp_hist_add(sh + p * kRadixSize, digit_of(k, plan.shift[p], (1u << plan.nbits[p]) - 1), valid, lane);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < P * kRadixSize; i += THREADS) {

@@ -109,6 +109,42 @@ pack_kernel(const SymT *__restrict__ T, u64 n, int b, u64 *__restrict__ words, u
     words[j] = w;
 }
 
+// Byte texts whose code width divides 8 (b = 1, 2, 4, 8: every word is a whole number of bytes of
+// text): 8-byte loads, codes from a shared-memory table (IDENT: the table is the identity -- all
+// 256 byte values occur -- and a word is just 8 text bytes in big-endian order).
+template <int B, bool IDENT>
+__global__ void __launch_bounds__(256)
+pack_bytes_kernel(const u8 *__restrict__ T, u64 n, u64 *__restrict__ words, u64 nwords, const u8 *__restrict__ lut)
+{
+    __shared__ u8 s_lut[256];
+    if (!IDENT) { s_lut[threadIdx.x] = lut[threadIdx.x]; __syncthreads(); }
+    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= nwords) return;
+    constexpr int SPW = 64 / B;                    // symbols (= text bytes) per word
+    const u64 s0 = j * SPW;
+    u64 w = 0;
+    if (s0 + SPW <= n && ((uintptr_t)T & 7) == 0) {
+        const u64 *T8 = reinterpret_cast<const u64 *>(T + s0);
+#pragma unroll
+        for (int q = 0; q < SPW / 8; ++q) {
+            const u64 x = T8[q];
+            if (IDENT) {
+                w = (u64)__byte_perm((u32)x, 0, 0x0123) << 32 | (u64)__byte_perm((u32)(x >> 32), 0, 0x0123);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) w = (w << B) | (u64)s_lut[(u32)(x >> (8 * t)) & 255];
+            }
+        }
+    } else {
+        for (int t = 0; t < SPW; ++t) {
+            const u64 sidx = s0 + t;
+            const u64 code = sidx < n ? (IDENT ? (u64)T[sidx] : (u64)s_lut[T[sidx]]) : 0;
+            w = (w << B) | code;
+        }
+    }
+    words[j] = w;
+}
+
 // k-mer of suffix p: the K most significant bits of the 64-bit window at bit p*b
 __device__ __forceinline__ u64 kmer_at(const u64 *__restrict__ words, u64 p, int b, int K)
 {
@@ -158,10 +194,11 @@ make_keys_kernel(const u64 *__restrict__ words, u64 n, int b, int K, int key_shi
 // scatter, compaction of non-singleton ("active") suffixes with their slot and dense group id,
 // and -- for suffixes that became singletons ("final") -- the fused outputs: BWT row byte,
 // primary index, aux samples.  Three kernels, no inter-CTA waiting:
-//   rank_flags  streaming: flags per element as warp ballots (3 words per 32 elements), per-warp
-//               and per-tile aggregates, and everything that needs no prefix: SA[slot], BWT rows,
-//               primary, aux samples
-//   rank_scan   one CTA: exclusive scan of the tile aggregates
+//   rank_flags  streaming, 4 consecutive elements per thread (16-byte loads; neighbour compares stay
+//               in the thread, one shuffle per thread for the element before / after): head and
+//               active bits (one byte per thread), per-warp and per-tile aggregates, and everything
+//               that needs no prefix: SA[slot], BWT rows, primary, aux samples
+//   rank_scan   three CTAs: exclusive scan of the tile aggregates
 //               [0] max : slot of the last group head   [1] sum : active suffixes   [2] sum : active groups
 //   rank_apply  streaming over the tiles that contain work: rank -> ISA, compaction of the actives
 // ---------------------------------------------------------------------------------------------
@@ -183,12 +220,48 @@ struct RankArgs {
     u64 aux_mask; int aux_shift; u32 *aux_I;
     u64 *primary;
     u32 *a_pos, *a_slot, *a_grp;
-    u32 *masks;              // [3][N/32]   head / active / active-head ballots
+    u32 *masks;              // one byte per 4 elements: head bits | active bits << 4
     u32 *wagg;               // [ntiles * kRankWarps][3]  per-warp aggregates
-    u32 *tagg;               // [ntiles][3] per-tile aggregates, overwritten by their exclusive scan
+    u32 *tagg;               // [3][ntiles] per-tile aggregates, overwritten by their exclusive scan
     u64 nchunks;             // ceil(N / 32)
     u64 ntiles; u64 *out_counts;
 };
+
+// 4 consecutive elements of an array: one 16-byte access per 4 words when the address allows it
+__device__ __forceinline__ void load4(const u64 *__restrict__ p, u64 j0, int nv, u64 (&o)[4])
+{
+    if (nv == 4 && ((uintptr_t)(p + j0) & 15) == 0) {
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(p + j0), y = *reinterpret_cast<const ulonglong2 *>(p + j0 + 2);
+        o[0] = x.x; o[1] = x.y; o[2] = y.x; o[3] = y.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = i < nv ? p[j0 + i] : 0;
+    }
+}
+__device__ __forceinline__ void load4(const u32 *__restrict__ p, u64 j0, int nv, u32 (&o)[4])
+{
+    if (nv == 4 && ((uintptr_t)(p + j0) & 15) == 0) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(p + j0);
+        o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = i < nv ? p[j0 + i] : 0;
+    }
+}
+__device__ __forceinline__ void store4(u32 *__restrict__ p, u64 j0, int nv, const u32 (&v)[4])
+{
+    if (nv == 4 && ((uintptr_t)(p + j0) & 15) == 0) {
+        *reinterpret_cast<uint4 *>(p + j0) = make_uint4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < nv) p[j0 + i] = v[i];
+    }
+}
+// element of a 4-array picked by the highest set bit of a nibble (selects, no local memory)
+__device__ __forceinline__ u32 top_of(u32 nib, const u32 (&v)[4])
+{
+    return (nib & 8u) ? v[3] : (nib & 4u) ? v[2] : (nib & 2u) ? v[1] : (nib & 1u) ? v[0] : 0u;
+}
 
 template <bool ROUND0>
 __global__ void __launch_bounds__(kRankThreads)
@@ -198,94 +271,87 @@ rank_flags_kernel(const RankArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 N = a.N;
     const u64 tile = blockIdx.x;
-    const u64 wbase = tile * kRankTile + (u64)warp * (kRankIPT * 32) + lane;
+    const u64 j0 = tile * kRankTile + (u64)tid * 4, jn = j0 + 4;       // my elements: [j0, j0 + nv)
+    const int nv = j0 < N ? (N - j0 < 4 ? (int)(N - j0) : 4) : 0;
+    const u32 vb = (1u << nv) - 1u;
 
-    // ---- all loads first (independent, latencies overlap).  Neighbours j-1 / j+1 come by shuffle;
-    // only lane 0 of the first item and lane 31 of the last item read across the warp's chunk.
-    u64 kk[kRankIPT]; u32 p[kRankIPT], slot[kRankIPT];
-    u32 pc[ROUND0 ? kRankIPT / 4 : 1] = {0};
+    u64 kk[4]; u32 p[4], slot[4];
+    load4(a.keys, j0, nv, kk);
+    load4(a.pos, j0, nv, p);
+    if (ROUND0) {
 #pragma unroll
-    for (int i = 0; i < kRankIPT; ++i) {
-        const u64 j = wbase + (u64)i * 32;
-        const bool valid = j < N;
-        const u64 kraw = valid ? a.keys[j] : 0;
-        kk[i] = kraw >> a.key_shift;
-        p[i] = valid ? a.pos[j] : 0;
-        slot[i] = ROUND0 ? a.slot_base + (u32)j : (valid ? a.slot_in[j] : 0);
-        if (ROUND0) pc[i >> 2] |= (u32)(kraw & 255) << (8 * (i & 3));
-    }
-    const u64 jfirst = wbase - lane, jlast = jfirst + kRankIPT * 32;      // chunk = [jfirst, jlast)
+        for (int i = 0; i < 4; ++i) slot[i] = a.slot_base + (u32)j0 + (u32)i;
+    } else load4(a.slot_in, j0, nv, slot);
+    // the elements just outside the warp's 128: lane 0 reads element j0 - 1, lane 31 element j0 + 4
     u64 kbefore = 0, kafter = 0; u32 pbefore = 0, pafter = 0;
-    if (lane == 0 && jfirst > 0 && jfirst < N) { kbefore = a.keys[jfirst - 1] >> a.key_shift; if (ROUND0) pbefore = a.pos[jfirst - 1]; }
-    if (lane == 31 && jlast < N) { kafter = a.keys[jlast] >> a.key_shift; if (ROUND0) pafter = a.pos[jlast]; }
+    if (lane == 0 && j0 > 0 && nv > 0) { kbefore = a.keys[j0 - 1] >> a.key_shift; if (ROUND0) pbefore = a.pos[j0 - 1]; }
+    if (lane == 31 && jn < N) { kafter = a.keys[jn] >> a.key_shift; if (ROUND0) pafter = a.pos[jn]; }
 
-    u32 hm[kRankIPT], tm[ROUND0 ? kRankIPT : 1];
+    u32 prevbytes = 0;
+    if (ROUND0) prevbytes = (u32)(kk[0] & 255) | (u32)(kk[1] & 255) << 8 | (u32)(kk[2] & 255) << 16 | (u32)(kk[3] & 255) << 24;
 #pragma unroll
-    for (int i = 0; i < kRankIPT; ++i) {
-        const u64 j = wbase + (u64)i * 32;
-        const bool valid = j < N;
-        u64 kprev = __shfl_up_sync(0xffffffffu, kk[i], 1);
-        const u64 carry = __shfl_sync(0xffffffffu, i ? kk[i ? i - 1 : 0] : kbefore, i ? 31 : 0);   // element j-1 of lane 0
-        if (lane == 0) kprev = carry;
-        hm[i] = __ballot_sync(0xffffffffu, valid && (j == 0 || kprev != kk[i]));
-        if (ROUND0) tm[i] = __ballot_sync(0xffffffffu, valid && (u64)p[i] >= a.tail_start);
-    }
-    // head flag of the element right after the chunk (for the last element's "next head")
-    const bool after_valid = jlast < N;
-    u32 after_head = 1, after_tail = 0, before_tail = 0;
-    {
-        u64 klast = __shfl_sync(0xffffffffu, kk[kRankIPT - 1], 31);
-        after_head = __shfl_sync(0xffffffffu, (u32)(!after_valid || kafter != klast), 31);
-        if (ROUND0) {
-            after_tail = __shfl_sync(0xffffffffu, (u32)(after_valid && (u64)pafter >= a.tail_start), 31);
-            before_tail = __shfl_sync(0xffffffffu, (u32)(jfirst > 0 && jfirst < N && (u64)pbefore >= a.tail_start), 0);
-        }
-    }
-    u32 vmask[kRankIPT];
-#pragma unroll
-    for (int i = 0; i < kRankIPT; ++i) vmask[i] = __ballot_sync(0xffffffffu, wbase + (u64)i * 32 < N);
+    for (int i = 0; i < 4; ++i) kk[i] >>= a.key_shift;
+    u64 kprev = __shfl_up_sync(0xffffffffu, kk[3], 1);
+    if (lane == 0) kprev = kbefore;
+    u32 h = (u32)(j0 == 0 || kprev != kk[0]) | (u32)(kk[0] != kk[1]) << 1 | (u32)(kk[1] != kk[2]) << 2 | (u32)(kk[2] != kk[3]) << 3;
+    h &= vb;
+    u32 t = 0;
     if (ROUND0) {
         // tail suffixes are singletons: they are heads, and so is the element after one
-#pragma unroll
-        for (int i = 0; i < kRankIPT; ++i) {
-            u32 prev_tail = (tm[i] << 1) | (i ? (tm[i ? i - 1 : 0] >> 31) : before_tail);
-            hm[i] |= tm[i] | (prev_tail & vmask[i]);
-        }
-        after_head |= after_tail | (tm[kRankIPT - 1] >> 31);
+        t = ((u32)((u64)p[0] >= a.tail_start) | (u32)((u64)p[1] >= a.tail_start) << 1
+             | (u32)((u64)p[2] >= a.tail_start) << 2 | (u32)((u64)p[3] >= a.tail_start) << 3) & vb;
+        u32 tprev = __shfl_up_sync(0xffffffffu, t >> 3, 1);
+        if (lane == 0) tprev = (u32)(j0 > 0 && nv > 0 && (u64)pbefore >= a.tail_start);
+        h |= t | (((t << 1) | tprev) & vb);
     }
-    u32 w_head = 0, w_act = 0, w_grp = 0;
-#pragma unroll
-    for (int i = 0; i < kRankIPT; ++i) {
-        const u64 j = wbase + (u64)i * 32;
-        const bool valid = j < N;
-        const u32 vm = vmask[i];
-        // next-head mask: head flag of element j+1; an element beyond N counts as a head
-        const u32 nh_in = (hm[i] >> 1) | ((i + 1 < kRankIPT ? (hm[i + 1 < kRankIPT ? i + 1 : 0] & 1u) : after_head) << 31);
-        const u32 nv = (vm >> 1) | ((i + 1 < kRankIPT ? (vmask[i + 1 < kRankIPT ? i + 1 : 0] & 1u) : (u32)after_valid) << 31);
-        const u32 nh = nh_in | ~nv;
-        const u32 am = vm & ~(hm[i] & nh);
-        const u32 gm = am & hm[i];
-        if (hm[i]) w_head = __shfl_sync(0xffffffffu, slot[i], 31 - __clz(hm[i]));   // slots ascend: the latest head wins
-        w_act += __popc(am);
-        w_grp += __popc(gm);
-        const u64 chunk = j >> 5;
-        if (lane == 0 && chunk < a.nchunks) {
-            a.masks[chunk] = hm[i]; a.masks[a.nchunks + chunk] = am; a.masks[2 * a.nchunks + chunk] = gm;
+    // head flag of the element after my last one; an element beyond N counts as a head
+    u32 hnext = __shfl_down_sync(0xffffffffu, (h & 1u) | (u32)(nv == 0), 1);
+    if (lane == 31) {
+        if (jn >= N) hnext = 1;
+        else {
+            hnext = (u32)(kafter != kk[3]);
+            if (ROUND0) hnext |= (u32)((u64)pafter >= a.tail_start) | (t >> 3);
         }
-        if (valid) {
-            const bool act = (am >> lane) & 1;
-            if (a.SA) a.SA[slot[i] - a.slot_base] = p[i];
-            if (a.rows) {
-                if (ROUND0) a.rows[slot[i]] = (u8)(pc[i >> 2] >> (8 * (i & 3)));
-                else if (!act && p[i] != 0) a.rows[slot[i]] = a.text[p[i] - 1];
+    }
+    const u32 nh = (((h | ~vb) >> 1) & 7u) | (hnext << 3);
+    const u32 am = vb & ~(h & nh);          // active: not (head followed by a head)
+    const u32 gm = am & h;                  // heads of active groups
+
+    if (nv) {
+        reinterpret_cast<u8 *>(a.masks)[j0 >> 2] = (u8)(h | (am << 4));
+        if (a.SA) {
+            if (ROUND0) store4(a.SA, j0, nv, p);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < nv) a.SA[slot[i] - a.slot_base] = p[i];
             }
-            if (!act) {
-                // final: this suffix's slot will never change again
+        }
+        if (a.rows) {
+            if (ROUND0) {
+                u8 *r = a.rows + slot[0];
+                if (nv == 4 && ((uintptr_t)r & 3) == 0) *reinterpret_cast<u32 *>(r) = prevbytes;
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (i < nv) r[i] = (u8)(prevbytes >> (8 * i));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < nv && !((am >> i) & 1u) && p[i] != 0) a.rows[slot[i]] = a.text[p[i] - 1];
+            }
+        }
+        const u32 fin = vb & ~am;           // final: the slot of this suffix will never change again
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if ((fin >> i) & 1u) {
                 if (p[i] == 0) *a.primary = (u64)slot[i] + 1;
                 if (a.aux_I && ((u64)p[i] & a.aux_mask) == 0) a.aux_I[p[i] >> a.aux_shift] = slot[i] + 1;
             }
         }
     }
+    // slots ascend with the element index: the latest head of the warp is the largest head slot
+    const u32 w_head = __reduce_max_sync(0xffffffffu, top_of(h, slot));
+    const u32 w_act = __reduce_add_sync(0xffffffffu, (u32)__popc(am));
+    const u32 w_grp = __reduce_add_sync(0xffffffffu, (u32)__popc(gm));
     if (lane == 0) {
         u32 *wa = a.wagg + (tile * kRankWarps + warp) * 3;
         wa[0] = w_head; wa[1] = w_act; wa[2] = w_grp;
@@ -300,9 +366,10 @@ rank_flags_kernel(const RankArgs a)
     }
 }
 
-// One CTA: exclusive scan of the tile aggregates in place (SoA: tagg[q * ntiles + tile]);
-// totals -> out_counts[0..1].  Each warp owns a contiguous segment of tiles and walks it 32
-// tiles at a time (coalesced loads, shuffle scan, running carry): reduce, combine, re-walk.
+// Three CTAs (one per aggregate): exclusive scan of the tile aggregates in place (SoA:
+// tagg[q * ntiles + tile]); totals -> out_counts[0..1].  Each warp owns a contiguous segment of
+// tiles and walks it 32 tiles at a time (coalesced loads, shuffle scan, running carry): reduce,
+// combine, re-walk.
 __device__ __forceinline__ u32 warp_incl_scan(u32 v, bool is_max, int lane)
 {
 #pragma unroll
@@ -313,46 +380,45 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, bool is_max, int lane)
     return v;
 }
 
+static const int kRankScanCtas = 3;
 __global__ void __launch_bounds__(1024)
 rank_scan_kernel(u32 *__restrict__ tagg, u64 ntiles, u64 *__restrict__ out_counts)
 {
-    __shared__ u32 s_tot[3][32];
+    __shared__ u32 s_tot[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int q = blockIdx.x;
+    const bool is_max = q == 0;
+    u32 *v = tagg + (u64)q * ntiles;
     const u64 per = ((ntiles + 31) / 32 + 31) / 32 * 32;          // tiles per warp, multiple of 32
     const u64 lo = (u64)warp * per, hi = lo + per < ntiles ? lo + per : ntiles;
-    for (int q = 0; q < 3; ++q) {
-        const bool is_max = q == 0;
+    {
         u32 r = 0;
-        for (u64 i = lo + lane; i < hi; i += 32) { u32 v = tagg[q * ntiles + i]; r = is_max ? (v > r ? v : r) : r + v; }
+        for (u64 i = lo + lane; i < hi; i += 32) { u32 x = v[i]; r = is_max ? (x > r ? x : r) : r + x; }
 #pragma unroll
         for (int off = 16; off; off >>= 1) { u32 o = __shfl_xor_sync(0xffffffffu, r, off); r = is_max ? (o > r ? o : r) : r + o; }
-        if (lane == 0) s_tot[q][warp] = r;
+        if (lane == 0) s_tot[warp] = r;
     }
     __syncthreads();
-    if (warp < 3) {
-        const bool is_max = warp == 0;
-        u32 v = s_tot[warp][lane];
-        u32 inc = warp_incl_scan(v, is_max, lane);
+    if (warp == 0) {
+        u32 x = s_tot[lane];
+        u32 inc = warp_incl_scan(x, is_max, lane);
         u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
         if (lane == 0) ex = 0;
-        s_tot[warp][lane] = ex;
-        if (lane == 31 && !is_max) out_counts[warp - 1] = inc;
+        s_tot[lane] = ex;
+        if (lane == 31 && !is_max) out_counts[q - 1] = inc;
     }
     __syncthreads();
-    for (int q = 0; q < 3; ++q) {
-        const bool is_max = q == 0;
-        u32 carry = s_tot[q][warp];
-        for (u64 base = lo; base < hi; base += 32) {
-            const u64 i = base + lane;
-            u32 v = i < hi ? tagg[q * ntiles + i] : 0;
-            u32 inc = warp_incl_scan(v, is_max, lane);
-            u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
-            if (lane == 0) ex = 0;
-            ex = is_max ? (ex > carry ? ex : carry) : ex + carry;
-            if (i < hi) tagg[q * ntiles + i] = ex;
-            u32 tot = __shfl_sync(0xffffffffu, inc, 31);
-            carry = is_max ? (tot > carry ? tot : carry) : carry + tot;
-        }
+    u32 carry = s_tot[warp];
+    for (u64 base = lo; base < hi; base += 32) {
+        const u64 i = base + lane;
+        u32 x = i < hi ? v[i] : 0;
+        u32 inc = warp_incl_scan(x, is_max, lane);
+        u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = 0;
+        ex = is_max ? (ex > carry ? ex : carry) : ex + carry;
+        if (i < hi) v[i] = ex;
+        u32 tot = __shfl_sync(0xffffffffu, inc, 31);
+        carry = is_max ? (tot > carry ? tot : carry) : carry + tot;
     }
 }
 
@@ -383,40 +449,45 @@ rank_apply_kernel(const RankArgs a)
         h = __shfl_sync(0xffffffffu, h, 0); x = __shfl_sync(0xffffffffu, x, 0); g = __shfl_sync(0xffffffffu, g, 0);
         c_head = h > c_head ? h : c_head; c_act += x; c_grp += g;
     }
-    const u64 wbase = tile * kRankTile + (u64)warp * (kRankIPT * 32) + lane;
-    const u32 lt = lanemask_lt(), le = lt | (1u << lane);
-    u32 p[kRankIPT], slot[kRankIPT], hm[kRankIPT], am[kRankIPT], gm[kRankIPT];
+    const u64 j0 = tile * kRankTile + (u64)tid * 4;
+    const int nv = j0 < N ? (N - j0 < 4 ? (int)(N - j0) : 4) : 0;
+    const u32 mb = nv ? reinterpret_cast<const u8 *>(a.masks)[j0 >> 2] : 0u;
+    const u32 h = mb & 15u, am = mb >> 4, gm = am & h;
+    u32 p[4], slot[4];
+    load4(a.pos, j0, nv, p);
+    if (ROUND0) {
 #pragma unroll
-    for (int i = 0; i < kRankIPT; ++i) {
-        const u64 j = wbase + (u64)i * 32;
-        const bool valid = j < N;
-        const u64 chunk = j >> 5;
-        const bool cv = chunk < a.nchunks;
-        hm[i] = cv ? a.masks[chunk] : 0; am[i] = cv ? a.masks[a.nchunks + chunk] : 0; gm[i] = cv ? a.masks[2 * a.nchunks + chunk] : 0;
-        p[i] = valid ? a.pos[j] : 0;
-        slot[i] = ROUND0 ? a.slot_base + (u32)j : (valid ? a.slot_in[j] : 0);
-    }
+        for (int i = 0; i < 4; ++i) slot[i] = a.slot_base + (u32)j0 + (u32)i;
+    } else load4(a.slot_in, j0, nv, slot);
+    // actives / active groups in the lanes before mine (counts <= 128: both in one word)
+    const u32 mine = (u32)__popc(am) | (u32)__popc(gm) << 16;
+    u32 inc = mine;
 #pragma unroll
-    for (int i = 0; i < kRankIPT; ++i) {
-        const u64 j = wbase + (u64)i * 32;
-        const u32 hle = hm[i] & le;
-        const u32 src = hle ? (31 - __clz(hle)) : 0;
-        const u32 hs = __shfl_sync(0xffffffffu, slot[i], src);
-        const u32 rank = hle ? hs : c_head;
-        if (j < N) {
-            const bool act = (am[i] >> lane) & 1;
-            if (a.pair_idx) { a.pair_idx[j] = p[i]; a.pair_val[j] = rank; }
-            else if (a.isa_all || act) a.ISA[p[i]] = rank;
-            if (act) {
-                const u32 o = c_act + __popc(am[i] & lt);
+    for (int off = 1; off < 32; off <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
+    const u32 e_act = c_act + ((inc - mine) & 0xFFFFu), e_grp = c_grp + ((inc - mine) >> 16);
+    // rank = slot of the nearest head at or before the element: in my nibble, else in the nearest lane below
+    // that has one, else carried into the warp
+    const u32 hb = __ballot_sync(0xffffffffu, h != 0) & lanemask_lt();
+    const u32 hs = __shfl_sync(0xffffffffu, top_of(h, slot), hb ? 31 - __clz(hb) : 0);
+    u32 cur = hb ? hs : c_head;
+    u32 rk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { if ((h >> i) & 1u) cur = slot[i]; rk[i] = cur; }
+    if (nv) {
+        if (a.pair_idx) { store4(a.pair_idx, j0, nv, p); store4(a.pair_val, j0, nv, rk); }
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (i < nv && (a.isa_all || ((am >> i) & 1u))) a.ISA[p[i]] = rk[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if ((am >> i) & 1u) {
+                const u32 o = e_act + (u32)__popc(am & ((1u << i) - 1u));
                 a.a_pos[o] = p[i];
                 a.a_slot[o] = slot[i];
-                a.a_grp[o] = c_grp + __popc(gm[i] & le) - 1;
+                a.a_grp[o] = e_grp + (u32)__popc(gm & ((2u << i) - 1u)) - 1;
             }
         }
-        if (hm[i]) c_head = __shfl_sync(0xffffffffu, slot[i], 31 - __clz(hm[i]));
-        c_act += __popc(am[i]);
-        c_grp += __popc(gm[i]);
     }
 }
 
@@ -437,25 +508,60 @@ __device__ __forceinline__ u32 lazy_rank(const LazyArgs &la, u64 q)
     return (u32)s;
 }
 
-// round >= 1 keys: (dense group id, rank of the suffix h positions further + 1)
+// round >= 1 keys: (dense group id, rank of the suffix h positions further + 1).  The ISA gather
+// leaves the issue slots idle, so the digit histograms of the sort that follows are taken here,
+// while the keys are in registers (hist[pass][256], zeroed by the caller): the sort needs no
+// histogram pass of its own.  Grid-stride over tiles of 1024 elements, 4 gathers in flight per thread.
+static const int kKeyPasses = 8;        // a 64-bit key has at most 8 digits
 template <bool LAZY>
 __global__ void __launch_bounds__(256)
 round_keys_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp,
                   const u32 *__restrict__ ISA, u64 N, u64 n, u64 h, int rank_bits,
-                  u64 *__restrict__ keys, u32 *__restrict__ pos, const LazyArgs la)
+                  u64 *__restrict__ keys, u32 *__restrict__ pos, const LazyArgs la,
+                  const SortPlan plan, u64 *__restrict__ hist)
 {
-    u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (j >= N) return;
-    u32 p = a_pos[j];
-    u64 q = (u64)p + h;
-    u64 k2 = 0;
-    if (q < n) {
-        u32 r = ISA[q];
-        if (LAZY && r == kIsaInvalid) r = lazy_rank(la, q);
-        k2 = (u64)r + 1;
+    __shared__ u32 sh[kKeyPasses * kRadixSize];
+    const int tid = threadIdx.x, lane = tid & 31, P = plan.passes;
+    for (int i = tid; i < P * kRadixSize; i += 256) sh[i] = 0;
+    __syncthreads();
+    for (u64 base = (u64)blockIdx.x * 1024; base < N; base += (u64)gridDim.x * 1024) {
+        u32 p[4], g[4], r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u64 j = base + (u64)i * 256 + tid;
+            p[i] = j < N ? a_pos[j] : 0;
+            g[i] = j < N ? a_grp[j] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u64 j = base + (u64)i * 256 + tid, q = (u64)p[i] + h;
+            r[i] = (j < N && q < n) ? ISA[q] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u64 j = base + (u64)i * 256 + tid, q = (u64)p[i] + h;
+            const bool valid = j < N;
+            u64 key = 0;
+            if (valid) {
+                u64 k2 = 0;
+                if (q < n) {
+                    u32 rr = r[i];
+                    if (LAZY && rr == kIsaInvalid) rr = lazy_rank(la, q);
+                    k2 = (u64)rr + 1;
+                }
+                key = ((u64)g[i] << rank_bits) | k2;
+                keys[j] = key;
+                pos[j] = p[i];
+            }
+            for (int d = 0; d < P; ++d)
+                warp_hist_add(sh + d * kRadixSize, digit_of(key, plan.shift[d], (1u << plan.nbits[d]) - 1), valid, lane);
+        }
     }
-    keys[j] = ((u64)a_grp[j] << rank_bits) | k2;
-    pos[j] = p;
+    __syncthreads();
+    for (int i = tid; i < P * kRadixSize; i += 256) {
+        const u32 cnt = sh[i];
+        if (cnt) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)cnt);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -582,6 +688,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     // ---- alphabet: bits per symbol, order-preserving code map (bytes), key width
     int b = 8; double entropy = 8.0;
     u8 *d_lut = nullptr;
+    bool lut_identity = false;
     if (sym_bytes == 1) {
         run_byte_histogram(c, (const u8 *)d_T, n);
         c.check(cudaMemcpyAsync(c.h_scalars + S_FREQ, c.d_scalars + S_FREQ, 256 * sizeof(u64),
@@ -594,6 +701,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             if (f) { lut[s] = (u8)sigma; ++sigma; double pr = (double)f / (double)n; entropy -= pr * std::log2(pr); }
         }
         b = bits_for((u64)(sigma > 1 ? sigma - 1 : 1));
+        lut_identity = sigma == 256;
         d_lut = c.alloc_n<u8>(256);
         if (!d_lut) return -2;
         // h_scalars tail as pinned staging for the LUT
@@ -637,7 +745,12 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     {
         u32 grid = (u32)ceil_div(nwords, 256);
         double ab = (double)n * sym_bytes + (double)nwords * 8;
-        if (sym_bytes == 1) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u8, true>), grid, 256, 0, (const u8 *)d_T, n, b, words, nwords, d_lut);
+        if (sym_bytes == 1 && b == 8 && lut_identity) LSC_LAUNCH(c, KC_PACK, ab, (pack_bytes_kernel<8, true>), grid, 256, 0, (const u8 *)d_T, n, words, nwords, d_lut);
+        else if (sym_bytes == 1 && b == 8) LSC_LAUNCH(c, KC_PACK, ab, (pack_bytes_kernel<8, false>), grid, 256, 0, (const u8 *)d_T, n, words, nwords, d_lut);
+        else if (sym_bytes == 1 && b == 4) LSC_LAUNCH(c, KC_PACK, ab, (pack_bytes_kernel<4, false>), grid, 256, 0, (const u8 *)d_T, n, words, nwords, d_lut);
+        else if (sym_bytes == 1 && b == 2) LSC_LAUNCH(c, KC_PACK, ab, (pack_bytes_kernel<2, false>), grid, 256, 0, (const u8 *)d_T, n, words, nwords, d_lut);
+        else if (sym_bytes == 1 && b == 1) LSC_LAUNCH(c, KC_PACK, ab, (pack_bytes_kernel<1, false>), grid, 256, 0, (const u8 *)d_T, n, words, nwords, d_lut);
+        else if (sym_bytes == 1) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u8, true>), grid, 256, 0, (const u8 *)d_T, n, b, words, nwords, d_lut);
         else if (sym_bytes == 4) LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u32, false>), grid, 256, 0, (const u32 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
         else LSC_LAUNCH(c, KC_PACK, ab, (pack_kernel<u64, false>), grid, 256, 0, (const u64 *)d_T, n, b, words, nwords, (const u8 *)nullptr);
     }
@@ -692,7 +805,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     ra.ntiles = rank_tiles; ra.out_counts = c.d_scalars + S_NACT;
     ra.pair_idx = nullptr; ra.pair_val = nullptr;
     LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
-    LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, 1, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
+    LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
     if (!read_round_scalars(c)) return -2;
     u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
     rs.n_groups = G;
@@ -731,11 +844,18 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
         const int grp_bits = bits_for(G > 1 ? G - 1 : 1);
         RoundStat r; r.h = h; r.n_active = N; r.key_bits = rank_bits + grp_bits; r.passes = 0; r.n_groups = 0;
-        if (lazy) LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel<true>, (u32)ceil_div(N, 256), 256, 0,
-                             a_pos, a_grp, ISA, N, n, h, rank_bits, rk0, rv0, la);
-        else      LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel<false>, (u32)ceil_div(N, 256), 256, 0,
-                             a_pos, a_grp, ISA, N, n, h, rank_bits, rk0, rv0, la);
-        where = RadixSort<u64, u32>::sort(c, rk0, rv0, rk1, rv1, N, 0, rank_bits + grp_bits, sort_temp, err, &r.passes);
+        {
+            const int key_bits = rank_bits + grp_bits;
+            const SortPlan plan = make_sort_plan(0, key_bits);
+            c.check(cudaMemsetAsync(sort_temp, 0, (size_t)kMaxPasses * kRadixSize * sizeof(u64), st));
+            const u64 want = ceil_div(N, 1024);
+            const u32 grid = (u32)(want < (u64)c.sm_count * 8 ? want : (u64)c.sm_count * 8);
+            if (lazy) LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel<true>, grid, 256, 0,
+                                 a_pos, a_grp, ISA, N, n, h, rank_bits, rk0, rv0, la, plan, (u64 *)sort_temp);
+            else      LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (4 + 4 + 4 + 12), round_keys_kernel<false>, grid, 256, 0,
+                                 a_pos, a_grp, ISA, N, n, h, rank_bits, rk0, rv0, la, plan, (u64 *)sort_temp);
+            where = RadixSort<u64, u32>::sort_from<NoGen>(c, NoGen(), rk0, rv0, rk1, rv1, N, 0, key_bits, sort_temp, err, &r.passes, true);
+        }
         if (where < 0) return -2;
         const u64 tiles = ceil_div(N, kRankTile);
         ra.keys = where ? rk1 : rk0; ra.pos = where ? rv1 : rv0; ra.slot_in = slot_cur; ra.N = N; ra.tail_start = 0; ra.key_shift = 0;
@@ -743,7 +863,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         u64 *other_k = where ? rk0 : rk1;                     // the ping-pong half not holding the sorted result
         ra.pair_idx = (u32 *)other_k; ra.pair_val = (u32 *)other_k + N;
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 4), rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
-        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, 1, 1024, 0, rtagg, tiles, c.d_scalars + S_NACT);
+        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, tiles, c.d_scalars + S_NACT);
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (4 + 4 + 8 + 12), rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
         {   // new ranks -> ISA; the sorted (key, pos) buffer is dead now and serves as partition scratch
             u64 *sorted_k = where ? rk1 : rk0;
@@ -862,11 +982,11 @@ int run_rank_stage(Ctx &c, const u64 *d_keys, const u32 *d_pos, const u32 *d_slo
     ra.out_counts = c.d_scalars + S_NACT;
     if (d_slot_in == nullptr) {
         LSC_LAUNCH(c, KC_RANK_INIT, (double)count * 16, rank_flags_kernel<true>, (u32)tiles, kRankThreads, 0, ra);
-        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, 1, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
+        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
         LSC_LAUNCH(c, KC_RANK_INIT, (double)count * 24, rank_apply_kernel<true>, (u32)tiles, kRankThreads, 0, ra);
     } else {
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)count * 20, rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
-        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, 1, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
+        LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)count * 28, rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
     }
     c.check(cudaMemcpyAsync(c.h_scalars + S_NACT, c.d_scalars + S_NACT, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c.stream));

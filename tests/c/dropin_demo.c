@@ -49,8 +49,14 @@ int main(int argc, char **argv)
     printf("libsais rc %d sa %016llx freq %016llx\n", (int)rc, (unsigned long long)fnv(SA, sizeof(int32_t) * (size_t)n), (unsigned long long)fnv(freq, sizeof(freq)));
     primary = libsais_bwt(T, U, A, n, 0, NULL);
     printf("bwt primary %d u %016llx\n", (int)primary, (unsigned long long)fnv(U, (size_t)n));
-    rc = libsais_bwt_aux(T, V, A, n, 0, NULL, 4, I + 0 * 0 + 0);
-    printf("bwt_aux rc %d I0 %d\n", (int)rc, (int)(n > 64 * 4 ? -1 : I[0]));
+    {
+        int32_t r = 2; while ((n - 1) / r + 1 > 64) r *= 2;          /* sampling rate: at most 64 samples */
+        rc = libsais_bwt_aux(T, V, A, n, 0, NULL, r, I);
+        printf("bwt_aux r %d rc %d I %016llx\n", (int)r, (int)rc, (unsigned long long)fnv(I, sizeof(int32_t) * (size_t)((n - 1) / r + 1)));
+        rc = libsais_unbwt_aux(V, U, A, n, NULL, r, I);
+        printf("unbwt_aux rc %d same %d\n", (int)rc, (int)(memcmp(U, T, (size_t)n) == 0));
+        primary = libsais_bwt(T, U, A, n, 0, NULL);
+    }
     rc = libsais_unbwt(U, V, A, n, NULL, primary);
     printf("unbwt rc %d same %d\n", (int)rc, (int)(memcmp(V, T, (size_t)n) == 0));
     rc = libsais_plcp(T, SA, P, n);
