@@ -544,7 +544,7 @@ struct RadixSort {
         KeyT *kin = ka, *kout = kb; ValT *vin = va, *vout = vb;
         int where = 0;
         for (int p = 0; p < plan.passes; ++p) {
-            c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * sizeof(u64), c.stream));
+            c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * (n < (1ull << 30) ? sizeof(u32) : sizeof(u64)), c.stream));   // u32 status words below 2^30 (launch_pass)
             const int shift = plan.shift[p]; const u32 dmask = (1u << plan.nbits[p]) - 1;
             if (p == 0 && Gen::kActive) pass<Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, tickets, err);
             else pass<NoGen>(c, NoGen(), kin, vin, kout, vout, n, shift, dmask, base + p * kRadixSize, status, tickets + p, err);

@@ -422,18 +422,20 @@ rank_scan_kernel(u32 *__restrict__ tagg, u64 ntiles, u64 *__restrict__ out_count
     }
 }
 
+static const int kApplyTiles = 4;
 template <bool ROUND0>
 __global__ void __launch_bounds__(kRankThreads)
 rank_apply_kernel(const RankArgs a)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 N = a.N;
-    const u64 tile = blockIdx.x;
+    // a CTA walks kApplyTiles consecutive tiles (no block-level synchronisation below: warps are independent)
+    for (u64 tile = (u64)blockIdx.x * kApplyTiles; tile < a.ntiles && tile < ((u64)blockIdx.x + 1) * kApplyTiles; ++tile) {
     // tiles without active suffixes have nothing to do unless every rank is wanted
     u32 t_head = a.tagg[tile], t_act = a.tagg[a.ntiles + tile], t_grp = a.tagg[2 * a.ntiles + tile];
     if (!a.isa_all) {
         const u32 next_act = tile + 1 < a.ntiles ? a.tagg[a.ntiles + tile + 1] : (u32)a.out_counts[0];
-        if (next_act == t_act) return;
+        if (next_act == t_act) continue;
     }
     // exclusive prefix of this warp inside the tile from the per-warp aggregates
     u32 c_head = t_head, c_act = t_act, c_grp = t_grp;
@@ -488,6 +490,7 @@ rank_apply_kernel(const RankArgs a)
                 a.a_grp[o] = e_grp + (u32)__popc(gm & ((2u << i) - 1u)) - 1;
             }
         }
+    }
     }
 }
 
@@ -825,11 +828,11 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         }
         if (lazy) {
             ra.isa_all = 0;
-            LSC_LAUNCH(c, KC_RANK_INIT, (double)N * 16, rank_apply_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+            LSC_LAUNCH(c, KC_RANK_INIT, (double)N * 16, rank_apply_kernel<true>, (u32)ceil_div(rank_tiles, kApplyTiles), kRankThreads, 0, ra);
         } else {
             // every rank is needed: (position, rank) pairs in slot order, then a locality-partitioned scatter
             ra.isa_all = 1; ra.pair_idx = (u32 *)ko; ra.pair_val = (u32 *)ko + n;
-            LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (4 + 8) + (double)N * 12, rank_apply_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+            LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (4 + 8) + (double)N * 12, rank_apply_kernel<true>, (u32)ceil_div(rank_tiles, kApplyTiles), kRankThreads, 0, ra);
             if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)ks, (u32 *)ks + n, n, n, ISA, sort_temp, err) != 0) return -2;
         }
     }
@@ -864,7 +867,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         ra.pair_idx = (u32 *)other_k; ra.pair_val = (u32 *)other_k + N;
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 4), rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
         LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, tiles, c.d_scalars + S_NACT);
-        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (4 + 4 + 8 + 12), rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (4 + 4 + 8 + 12), rank_apply_kernel<false>, (u32)ceil_div(tiles, kApplyTiles), kRankThreads, 0, ra);
         {   // new ranks -> ISA; the sorted (key, pos) buffer is dead now and serves as partition scratch
             u64 *sorted_k = where ? rk1 : rk0;
             if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)sorted_k, (u32 *)sorted_k + N, N, n, ISA, sort_temp, err) != 0) return -2;
@@ -983,11 +986,11 @@ int run_rank_stage(Ctx &c, const u64 *d_keys, const u32 *d_pos, const u32 *d_slo
     if (d_slot_in == nullptr) {
         LSC_LAUNCH(c, KC_RANK_INIT, (double)count * 16, rank_flags_kernel<true>, (u32)tiles, kRankThreads, 0, ra);
         LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
-        LSC_LAUNCH(c, KC_RANK_INIT, (double)count * 24, rank_apply_kernel<true>, (u32)tiles, kRankThreads, 0, ra);
+        LSC_LAUNCH(c, KC_RANK_INIT, (double)count * 24, rank_apply_kernel<true>, (u32)ceil_div(tiles, kApplyTiles), kRankThreads, 0, ra);
     } else {
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)count * 20, rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
         LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, tagg, tiles, c.d_scalars + S_NACT);
-        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)count * 28, rank_apply_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
+        LSC_LAUNCH(c, KC_RANK_UPDATE, (double)count * 28, rank_apply_kernel<false>, (u32)ceil_div(tiles, kApplyTiles), kRankThreads, 0, ra);
     }
     c.check(cudaMemcpyAsync(c.h_scalars + S_NACT, c.d_scalars + S_NACT, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c.stream));
     if (!c.sync() || c.failed()) return -2;
