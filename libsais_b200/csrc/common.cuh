@@ -40,13 +40,14 @@ enum KernelClass {
     KC_UNBWT_WALK,     // unBWT: splitter walks
     KC_UNBWT_RANK,     // unBWT: splitter list ranking
     KC_CONVERT,        // widen / narrow / copy helpers
+    KC_LOCAL_SORT,     // round>=1 in-shared-memory sort of small groups (key build + sort in one kernel)
     KC_COUNT
 };
 
 static const char *const kKernelClassName[KC_COUNT] = {
     "hist_sym", "pack", "make_keys", "sort_hist", "sort_scan", "sort_pass", "sort_pass_gen", "rank_init", "rank_scan",
     "round_keys", "rank_update", "scatter", "bwt", "phi", "plcp", "lcp",
-    "unbwt_prep", "unbwt_walk", "unbwt_rank", "convert"
+    "unbwt_prep", "unbwt_walk", "unbwt_rank", "convert", "local_sort"
 };
 
 #ifdef __CUDACC__

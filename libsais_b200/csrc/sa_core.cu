@@ -25,6 +25,7 @@
 #include "core.h"
 #include "radix_sort.cuh"
 #include "scatter.cuh"
+#include "local_sort.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -674,7 +675,7 @@ static int choose_key_symbols(u64 n, int b, double entropy_bits, int max_key_bit
 
 static bool read_round_scalars(Ctx &c)
 {
-    c.check(cudaMemcpyAsync(c.h_scalars + S_ERR, c.d_scalars + S_ERR, (S_PRIMARY - S_ERR + 1) * sizeof(u64),
+    c.check(cudaMemcpyAsync(c.h_scalars + S_ERR, c.d_scalars + S_ERR, (S_BIGGRP - S_ERR + 1) * sizeof(u64),
                             cudaMemcpyDeviceToHost, c.stream));
     if (!c.sync()) return false;
     if (c.h_scalars[S_ERR] != 0) { c.last_error = cudaErrorLaunchTimeout; return false; }
@@ -843,11 +844,42 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     const int rank_bits = bits_for(n);                 // k2 = ISA+1 <= n
     u64 h = (u64)k;
     int round = 1;
+    // Rounds whose groups are all small are sorted where they lie (local_sort.cuh); a round with a large
+    // group, few active suffixes, or the lazy ISA takes the global onesweep.
+    bool local_on = true;
+    { const char *env = getenv("LIBSAIS_CUDA_LOCAL_SORT"); if (env && *env) local_on = atoi(env) != 0; }
+    local_on = local_on && !lazy;
+    const u64 kLocalMin = (u64)1 << 18;
+    auto launch_big_check = [&](u64 n_upper) {
+        c.check(cudaMemsetAsync(c.d_scalars + S_BIGGRP, 0, sizeof(u64), st));
+        const u64 want = ceil_div(n_upper, 256 * 8);
+        const u32 grid = (u32)(want < (u64)c.sm_count * 16 ? (want ? want : 1) : (u64)c.sm_count * 16);
+        LSC_LAUNCH(c, KC_LOCAL_SORT, 0.0, big_group_kernel, grid, 256, 0, a_grp, c.d_scalars + S_NACT, c.d_scalars + S_BIGGRP);
+    };
+    // window of a local-sort tile from the group-size flags (0: some group is too large for a tile)
+    auto local_window = [&]() -> u32 {
+        const u64 f = c.h_scalars[S_BIGGRP];
+        for (int i = 0; i < 3; ++i) if (!((f >> i) & 1)) return (u32)kLocalCap - kLocalLimits[i];
+        return 0;
+    };
+    u32 win = 0;
+    if (local_on && N >= kLocalMin) {
+        c.check(cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocalSmem)));
+        launch_big_check(N);
+        if (!read_round_scalars(c)) return -2;
+        win = local_window();
+    }
     while (N > 0) {
         if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
         const int grp_bits = bits_for(G > 1 ? G - 1 : 1);
         RoundStat r; r.h = h; r.n_active = N; r.key_bits = rank_bits + grp_bits; r.passes = 0; r.n_groups = 0;
-        {
+        const bool local = local_on && win != 0 && N >= kLocalMin;
+        if (local) {
+            // key build + sort in one kernel, in place of round_keys + onesweep (r.passes stays 0)
+            LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_sort_kernel, (u32)ceil_div(N, win), kLocalThreads, sizeof(LocalSmem),
+                       a_pos, a_grp, ISA, N, n, h, rank_bits, win, rk1, rv1, err);
+            where = 1;
+        } else {
             const int key_bits = rank_bits + grp_bits;
             const SortPlan plan = make_sort_plan(0, key_bits);
             c.check(cudaMemsetAsync(sort_temp, 0, (size_t)kMaxPasses * kRadixSize * sizeof(u64), st));
@@ -872,8 +904,11 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             u64 *sorted_k = where ? rk1 : rk0;
             if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)sorted_k, (u32 *)sorted_k + N, N, n, ISA, sort_temp, err) != 0) return -2;
         }
+        const bool checked = local_on && N >= kLocalMin;
+        if (checked) launch_big_check(N);
         if (!read_round_scalars(c)) return -2;
         N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
+        win = checked ? local_window() : 0;
         r.n_groups = G;
         c.rounds.push_back(r);
         u32 *t = slot_cur; slot_cur = slot_nxt; slot_nxt = t;

@@ -152,6 +152,28 @@ def test_forced_isa_modes_agree(cu):
         os.environ.pop("LIBSAIS_CUDA_LAZY_ISA", None)
 
 
+def test_local_and_global_round_sorts_agree(cu):
+    """Rounds >= 1 sort small groups inside shared memory (local_sort.cuh) or with the global onesweep: both
+    must give the oracle's SA.  Inputs: many small groups (mutated copies), a mix where one long repeat makes a
+    large group for a few rounds (global rounds first, local rounds later), and groups just around the tile size."""
+    import os
+    o = _libs.oracle()
+    rep = gen.repetitive_dna(40000, 60)                                    # 2.4 M, groups of <= 60
+    big = np.concatenate([gen.dna(11, 700000), np.zeros(5000, dtype=np.uint8) + 65, gen.dna(11, 700000), gen.dna(12, 300000)])
+    blocky = np.tile(gen.dna(13, 1100), 2049)[: 2200000]                   # ~2049 copies: groups just above the tile size, shrinking at the end
+    try:
+        for T in (rep, big, blocky):
+            want = o.sa(T)[1]
+            for mode in ("1", "0"):
+                os.environ["LIBSAIS_CUDA_LOCAL_SORT"] = mode
+                os.environ["LIBSAIS_CUDA_LAZY_ISA"] = "0"
+                rc, SA = cu.sa(T)
+                assert rc == 0 and (SA == want).all(), (len(T), mode)
+    finally:
+        os.environ.pop("LIBSAIS_CUDA_LOCAL_SORT", None)
+        os.environ.pop("LIBSAIS_CUDA_LAZY_ISA", None)
+
+
 def test_adversarial_periodic_inputs_vs_oracle(cu):
     o = _libs.oracle()
     for T in (np.zeros(1 << 17, dtype=np.uint8), np.resize(np.frombuffer(b"ab", dtype=np.uint8), (1 << 17) + 1),
