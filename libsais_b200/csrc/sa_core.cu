@@ -857,9 +857,10 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         LSC_LAUNCH(c, KC_LOCAL_SORT, 0.0, big_group_kernel, grid, 256, 0, a_grp, c.d_scalars + S_NACT, c.d_scalars + S_BIGGRP);
     };
     // window of a local-sort tile from the group-size flags (0: some group is too large for a tile)
-    auto local_window = [&]() -> u32 {
+    auto local_window = [&]() -> u32 {          // 1: every group fits the counting kernel
         const u64 f = c.h_scalars[S_BIGGRP];
-        for (int i = 0; i < 3; ++i) if (!((f >> i) & 1)) return (u32)kLocalCap - kLocalLimits[i];
+        if (!(f & 1)) return 1;
+        for (int i = 0; i < 3; ++i) if (!((f >> (i + 1)) & 1)) return (u32)kLocalCap - kLocalLimits[i];
         return 0;
     };
     u32 win = 0;
@@ -876,8 +877,10 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         const bool local = local_on && win != 0 && N >= kLocalMin;
         if (local) {
             // key build + sort in one kernel, in place of round_keys + onesweep (r.passes stays 0)
-            LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_sort_kernel, (u32)ceil_div(N, win), kLocalThreads, sizeof(LocalSmem),
-                       a_pos, a_grp, ISA, N, n, h, rank_bits, win, rk1, rv1, err);
+            if (win == 1) LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_count_kernel, (u32)ceil_div(N, kCountWindow), kCountThreads, 0,
+                                     a_pos, a_grp, ISA, N, n, h, rank_bits, rk1, rv1, err);
+            else LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_sort_kernel, (u32)ceil_div(N, win), kLocalThreads, sizeof(LocalSmem),
+                            a_pos, a_grp, ISA, N, n, h, rank_bits, win, rk1, rv1, err);
             where = 1;
         } else {
             const int key_bits = rank_bits + grp_bits;
