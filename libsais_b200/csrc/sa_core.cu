@@ -217,6 +217,7 @@ struct RankArgs {
     u32 *SA;                 // nullable: SA[slot - slot_base] = pos
     u32 *ISA; int isa_all;   // isa_all: write every element's rank, else only the active ones
     u32 *pair_idx, *pair_val; // non-null: emit (position, rank) pairs in element order instead of scattering into ISA
+    u64 *phist; int pshift;   // non-null: histogram of (position >> pshift) & 255 over the pairs, for the partition pass of the scatter
     u8 *rows; const u8 *text;            // BWT mode: rows[slot] = byte preceding the suffix
     u64 aux_mask; int aux_shift; u32 *aux_I;
     u64 *primary;
@@ -430,7 +431,10 @@ rank_apply_kernel(const RankArgs a)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 N = a.N;
-    // a CTA walks kApplyTiles consecutive tiles (no block-level synchronisation below: warps are independent)
+    __shared__ u32 s_ph[kRadixSize];
+    const bool ph = a.phist != nullptr && a.pair_idx != nullptr;
+    if (ph) { s_ph[tid] = 0; __syncthreads(); }
+    // a CTA walks kApplyTiles consecutive tiles (no block-level synchronisation inside: warps are independent)
     for (u64 tile = (u64)blockIdx.x * kApplyTiles; tile < a.ntiles && tile < ((u64)blockIdx.x + 1) * kApplyTiles; ++tile) {
     // tiles without active suffixes have nothing to do unless every rank is wanted
     u32 t_head = a.tagg[tile], t_act = a.tagg[a.ntiles + tile], t_grp = a.tagg[2 * a.ntiles + tile];
@@ -477,7 +481,13 @@ rank_apply_kernel(const RankArgs a)
 #pragma unroll
     for (int i = 0; i < 4; ++i) { if ((h >> i) & 1u) cur = slot[i]; rk[i] = cur; }
     if (nv) {
-        if (a.pair_idx) { store4(a.pair_idx, j0, nv, p); store4(a.pair_val, j0, nv, rk); }
+        if (a.pair_idx) {
+            store4(a.pair_idx, j0, nv, p); store4(a.pair_val, j0, nv, rk);
+            if (ph) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < nv) atomicAdd(&s_ph[(p[i] >> a.pshift) & 255u], 1u);
+            }
+        }
         else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) if (i < nv && (a.isa_all || ((am >> i) & 1u))) a.ISA[p[i]] = rk[i];
@@ -492,6 +502,11 @@ rank_apply_kernel(const RankArgs a)
             }
         }
     }
+    }
+    if (ph) {
+        __syncthreads();
+        const u32 v = s_ph[tid];
+        if (v) atomicAdd((unsigned long long *)&a.phist[tid], (unsigned long long)v);
     }
 }
 
@@ -807,7 +822,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     ra.a_pos = a_pos; ra.a_slot = slot_cur; ra.a_grp = a_grp;
     ra.masks = rmasks; ra.wagg = rwagg; ra.tagg = rtagg; ra.nchunks = ceil_div(n, 32);
     ra.ntiles = rank_tiles; ra.out_counts = c.d_scalars + S_NACT;
-    ra.pair_idx = nullptr; ra.pair_val = nullptr;
+    ra.pair_idx = nullptr; ra.pair_val = nullptr; ra.phist = nullptr; ra.pshift = 0;
     LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
     LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
     if (!read_round_scalars(c)) return -2;
@@ -833,8 +848,10 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         } else {
             // every rank is needed: (position, rank) pairs in slot order, then a locality-partitioned scatter
             ra.isa_all = 1; ra.pair_idx = (u32 *)ko; ra.pair_val = (u32 *)ko + n;
+            const bool fused_hist = scatter_hist_prepare(c, n, n, sort_temp, &ra.phist, &ra.pshift);
             LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (4 + 8) + (double)N * 12, rank_apply_kernel<true>, (u32)ceil_div(rank_tiles, kApplyTiles), kRankThreads, 0, ra);
-            if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)ks, (u32 *)ks + n, n, n, ISA, sort_temp, err) != 0) return -2;
+            if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)ks, (u32 *)ks + n, n, n, ISA, sort_temp, err, fused_hist) != 0) return -2;
+            ra.phist = nullptr;
         }
     }
     LazyArgs la; la.words = words; la.b = b; la.K = K; la.s0_keys = ks; la.s0_pos = vs; la.key_shift = key_shift;
@@ -900,13 +917,15 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         ra.isa_all = 1; ra.a_slot = slot_nxt; ra.ntiles = tiles; ra.nchunks = ceil_div(N, 32);
         u64 *other_k = where ? rk0 : rk1;                     // the ping-pong half not holding the sorted result
         ra.pair_idx = (u32 *)other_k; ra.pair_val = (u32 *)other_k + N;
+        const bool fused_hist = scatter_hist_prepare(c, N, n, sort_temp, &ra.phist, &ra.pshift);
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (12 + 4 + 4), rank_flags_kernel<false>, (u32)tiles, kRankThreads, 0, ra);
         LSC_LAUNCH(c, KC_RANK_SCAN, (double)tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, tiles, c.d_scalars + S_NACT);
         LSC_LAUNCH(c, KC_RANK_UPDATE, (double)N * (4 + 4 + 8 + 12), rank_apply_kernel<false>, (u32)ceil_div(tiles, kApplyTiles), kRankThreads, 0, ra);
         {   // new ranks -> ISA; the sorted (key, pos) buffer is dead now and serves as partition scratch
             u64 *sorted_k = where ? rk1 : rk0;
-            if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)sorted_k, (u32 *)sorted_k + N, N, n, ISA, sort_temp, err) != 0) return -2;
+            if (partitioned_scatter<NoGen>(c, NoGen(), ra.pair_idx, ra.pair_val, (u32 *)sorted_k, (u32 *)sorted_k + N, N, n, ISA, sort_temp, err, fused_hist) != 0) return -2;
         }
+        ra.phist = nullptr;
         const bool checked = local_on && N >= kLocalMin;
         if (checked) launch_big_check(N);
         if (!read_round_scalars(c)) return -2;
@@ -1016,7 +1035,7 @@ int run_rank_stage(Ctx &c, const u64 *d_keys, const u32 *d_pos, const u32 *d_slo
     ra.keys = d_keys; ra.pos = d_pos; ra.slot_in = d_slot_in; ra.N = count; ra.tail_start = ~0ull; ra.key_shift = 0;
     ra.slot_base = slot_base;
     ra.SA = d_sa_local; ra.ISA = nullptr; ra.isa_all = 1; ra.pair_idx = d_pair_pos; ra.pair_val = d_pair_rank;
-    ra.rows = nullptr; ra.text = nullptr; ra.aux_mask = 0; ra.aux_shift = 0; ra.aux_I = nullptr;
+    ra.rows = nullptr; ra.text = nullptr; ra.aux_mask = 0; ra.aux_shift = 0; ra.aux_I = nullptr; ra.phist = nullptr; ra.pshift = 0;
     ra.primary = c.d_scalars + S_PRIMARY;
     ra.a_pos = d_act_pos; ra.a_slot = d_act_slot; ra.a_grp = d_act_grp;
     ra.masks = masks; ra.wagg = wagg; ra.tagg = tagg; ra.nchunks = ceil_div(count, 32); ra.ntiles = tiles;

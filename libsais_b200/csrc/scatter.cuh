@@ -30,14 +30,32 @@ scatter_gen_kernel(const Gen gen, u64 N, u32 *__restrict__ dst, u64 dst_len)
     if ((u64)p < dst_len) dst[p] = gen.val(i);
 }
 
+static inline bool scatter_is_direct(u64 N, u64 dst_len) { return dst_len <= (8ull << 20) || N < (1ull << 20); }
+
+// The producer of the pairs can take the histogram of the partition digit itself (one shared-memory add per
+// pair while the position is in a register) and save the partition pass its read of the index array: zeroes
+// the histogram slot of `sort_temp` and returns where to count and the digit's shift; false when the scatter
+// will be direct and needs no histogram.
+static inline bool scatter_hist_prepare(Ctx &c, u64 N, u64 dst_len, void *sort_temp, u64 **hist, int *shift)
+{
+    *hist = nullptr; *shift = 0;
+    if (N == 0 || scatter_is_direct(N, dst_len)) return false;
+    const int bits = bits_for(dst_len - 1);
+    *shift = bits > kRadixBits ? bits - kRadixBits : 0;
+    *hist = (u64 *)sort_temp;
+    c.check(cudaMemsetAsync(sort_temp, 0, kRadixSize * sizeof(u64), c.stream));
+    return true;
+}
+
 // Pairs come from (ia, va), or from `gen` when Gen::kActive.  (ib, vb): N-element scratch.
 // Small problems (destination fits L2 comfortably, or few pairs) scatter directly.
+// hist_ready: the digit histogram is already in `sort_temp` (scatter_hist_prepare + the producer).
 template <typename Gen>
 static int partitioned_scatter(Ctx &c, const Gen &gen, u32 *ia, u32 *va, u32 *ib, u32 *vb, u64 N, u64 dst_len,
-                               u32 *dst, void *sort_temp, u32 *err)
+                               u32 *dst, void *sort_temp, u32 *err, bool hist_ready = false)
 {
     if (N == 0) return 0;
-    const bool direct = dst_len <= (8ull << 20) || N < (1ull << 20) || ib == nullptr || vb == nullptr;
+    const bool direct = scatter_is_direct(N, dst_len) || ib == nullptr || vb == nullptr;
     if (direct) {
         const int kc = c.pass_class_override >= 0 ? c.pass_class_override : KC_SCATTER;
         if (Gen::kActive) LSC_LAUNCH(c, kc, (double)N * 12, scatter_gen_kernel<Gen>, (u32)ceil_div(N, 256), 256, 0, gen, N, dst, dst_len);
@@ -49,7 +67,7 @@ static int partitioned_scatter(Ctx &c, const Gen &gen, u32 *ia, u32 *va, u32 *ib
     const int saved_class = c.pass_class_override;
     const int kc = saved_class >= 0 ? saved_class : KC_SCATTER;
     c.pass_class_override = kc;
-    int where = RadixSort<u32, u32>::template sort_from<Gen>(c, gen, ia, va, ib, vb, N, lo, bits, sort_temp, err);
+    int where = RadixSort<u32, u32>::template sort_from<Gen>(c, gen, ia, va, ib, vb, N, lo, bits, sort_temp, err, nullptr, hist_ready);
     c.pass_class_override = saved_class;
     if (where != 1) return -2;
     LSC_LAUNCH(c, kc, (double)N * 12, scatter_pairs_kernel, (u32)ceil_div(N, 256), 256, 0, ib, vb, N, dst, dst_len);
