@@ -14,7 +14,9 @@
 //                 SA / BWT rows / primary / aux outputs, compaction of the suffixes whose group is
 //                 not yet a singleton ("active"); ranks reach ISA through the locality-partitioned
 //                 scatter (scatter.cuh) -- or not at all when few suffixes stay active (lazy ISA)
-//   repeat while active: round_keys (g, ISA[p+h]+1) -> onesweep -> rank stage; h doubles
+//   repeat while active: keys (g, ISA[p+h]+1), sorted -> rank stage; h doubles.  Rounds whose groups are
+//                 all small gather and sort them inside shared memory (local_sort.cuh: counting rank or
+//                 in-tile radix passes); the others run round_keys (+ digit histograms) -> onesweep
 //   (bottom of the file: building blocks of the distributed variant, libsais_b200/dist.py)
 //
 // End-of-text rule ("a suffix that is a prefix of another sorts first", reference
