@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path, called through the C-ABI of libsais_cuda.so exactly as a C
 program would call the reference, must be bit-exact with the committed golden vectors, with
 the oracle, and (where oracle/_ref travelled to the box) with the unmodified reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -172,6 +174,16 @@ def test_local_and_global_round_sorts_agree(cu):
     finally:
         os.environ.pop("LIBSAIS_CUDA_LOCAL_SORT", None)
         os.environ.pop("LIBSAIS_CUDA_LAZY_ISA", None)
+
+
+def test_seeded_stress_differential(cu, capsys):
+    """15 s of tools/stress.py: random structured texts (copies, runs, periodic, skewed, exact repeats) with the
+    route-forcing knobs flipped at random, SA / BWT (+ PLCP / LCP / unBWT on a sample) against the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress.py"), "15", "7"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and '"stress": "ok"' in r.stdout, (r.stdout[-500:], r.stderr[-500:])
 
 
 def test_adversarial_periodic_inputs_vs_oracle(cu):
