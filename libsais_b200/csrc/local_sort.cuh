@@ -4,11 +4,19 @@
 // round only has to order each group by the rank of the suffix h positions further -- nothing
 // moves between groups.  When no group is larger than 2048 elements the global onesweep
 // (7 digit passes over (u64,u32) pairs in HBM at n ~ 2^31, each with its look-back) is replaced
-// by one kernel: a CTA takes the groups that START in a window [t*C, (t+1)*C) of the active list --
-// at most kLocalCap elements, see kLocalLimits -- gathers their keys (the ISA look-up of round_keys_kernel is fused in), sorts the tile in shared
-// memory by (group id relative to the tile, rank) with the same stable ballot multisplit as the
-// global pass, and writes (key, position) back in place.  The number of digit passes adapts to the
-// tile: bits(rank) + bits(groups in the tile).  One read and one write of the active list per round.
+// by ONE kernel: a CTA takes the groups that START in a window [t*C, (t+1)*C) of the active list
+// (whole groups, at most the tile capacity: find_tile), gathers their keys -- the ISA look-up of
+// round_keys_kernel is fused in -- orders them in shared memory and writes (key, position) back
+// in place.  One read and one write of the active list per round.
+//   local_count_kernel  no group > 128: every element counts the members of its group that
+//                       precede it (s compares for a group of s, no barriers), small tiles,
+//                       5-7 CTAs per SM
+//   local_sort_kernel   groups up to 2048: stable 8-bit LSD passes inside shared memory with the
+//                       ballot multisplit of the global pass, as many as the tile needs
+//                       (bits(rank) + bits(groups in the tile)); tiles that happen to hold only
+//                       small groups take the counting path
+// big_group_kernel classifies the round (largest group vs 128 / 512 / 1024 / 2048); build_sa
+// (sa_core.cu) picks the kernel and the window, or falls back to the global sort.
 #pragma once
 #include "radix_sort.cuh"
 
