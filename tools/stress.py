@@ -1,5 +1,6 @@
 """Seeded differential stress of the CUDA library against the oracle (run on a GPU box):
-   python tools/stress.py [seconds] [seed]
+   python tools/stress.py [seconds] [seed] [big]
+("big": texts of 2^20 .. 2^24 symbols made of copies / runs / repeats only -- many tiles per local-sort round)
 Random texts with structure that exercises every route through the prefix doubling -- many small groups (local
 counting sort), groups of hundreds to thousands (in-tile radix), giant groups (global onesweep), few active
 suffixes (lazy ISA) -- with the route-forcing environment knobs flipped at random.  Compares SA, BWT + primary
@@ -17,9 +18,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _libs  # noqa: E402
 
 
-def make_text(rng):
+def make_text(rng, big=False):
     kind = rng.integers(0, 7)
     n = int(2 ** rng.uniform(4, 21.5))
+    if big:
+        kind = int(rng.choice([1, 1, 1, 3, 4]))
+        n = int(2 ** rng.uniform(20, 24))
     sigma = int(rng.choice([1, 2, 3, 4, 5, 16, 26, 64, 200, 256]))
     if kind == 0:                                   # iid
         T = rng.integers(0, sigma, n)
@@ -53,11 +57,12 @@ def make_text(rng):
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"
     rng = np.random.default_rng(seed)
     cu, o = _libs.cuda(), _libs.oracle()
     t0, cases, symbols = time.time(), 0, 0
     while time.time() - t0 < budget:
-        kind, T = make_text(rng)
+        kind, T = make_text(rng, big)
         env = {}
         if rng.random() < 0.5: env["LIBSAIS_CUDA_LOCAL_SORT"] = str(int(rng.integers(0, 2)))
         if rng.random() < 0.5: env["LIBSAIS_CUDA_LAZY_ISA"] = str(int(rng.integers(0, 2)))
