@@ -41,13 +41,15 @@ enum KernelClass {
     KC_UNBWT_RANK,     // unBWT: splitter list ranking
     KC_CONVERT,        // widen / narrow / copy helpers
     KC_LOCAL_SORT,     // round>=1 in-shared-memory sort of small groups (key build + sort in one kernel)
+    KC_PART_PASS,      // unstable digit partition pass (round-0 MSD levels; the stable pass is KC_SORT_PASS)
+    KC_BUCKET_SORT,    // round-0 MSD finish: every 16-bit bucket sorted inside shared memory
     KC_COUNT
 };
 
 static const char *const kKernelClassName[KC_COUNT] = {
     "hist_sym", "pack", "make_keys", "sort_hist", "sort_scan", "sort_pass", "sort_pass_gen", "rank_init", "rank_scan",
     "round_keys", "rank_update", "scatter", "bwt", "phi", "plcp", "lcp",
-    "unbwt_prep", "unbwt_walk", "unbwt_rank", "convert", "local_sort"
+    "unbwt_prep", "unbwt_walk", "unbwt_rank", "convert", "local_sort", "part_pass", "bucket_sort"
 };
 
 #ifdef __CUDACC__

@@ -56,54 +56,166 @@ struct PhiGen {
 
 // ---------------------------------------------------------------------------------------------
 // PLCP compare (reference compute_plcp :8167-8190, _int :8263-8286): in text order,
-// PLCP[i] = lcp(T[i..], T[phi[i]..]) with the Kasai carry PLCP[i] >= PLCP[i-1]-1 kept inside
-// each thread's chunk of consecutive positions; bytes are compared 8 at a time through
-// unaligned 64-bit windows assembled from aligned loads.
+// PLCP[i] = lcp(T[i..], T[phi[i]..]).  The Kasai bound PLCP[i] >= PLCP[i-1] - 1 generalises to
+// PLCP[i] >= PLCP[i-s] - s, which is what makes the work O(n log n) in the WORST case with
+// n-way parallelism (a chunk that restarted at l = 0 cost O(PLCP) per chunk: quadratic on a^n):
+//   1. position 0, then levels s = 2^L .. kPlcpChunk: every odd multiple i of s is computed by one
+//      WARP (16 bytes per lane and step) starting from the bound given by the already known
+//      PLCP[i - s]; per level the compares telescope to <= 2n symbols.  phi[i] is read from
+//      PLCP[i] itself, which is overwritten in place.
+//   2. the chunk kernel: every thread walks kPlcpChunk consecutive positions from its (now exact)
+//      chunk head with the l - 1 carry; the warp's 1024 phi/PLCP values are staged through shared
+//      memory so global accesses are coalesced; bytes are compared 16 at a time through
+//      unaligned windows built from aligned 8-byte loads.
 // ---------------------------------------------------------------------------------------------
 static const int kPlcpChunk = 32;
+static const int kPlcpThreads = 128;
 
-__device__ __forceinline__ u64 window64(const u64 *__restrict__ W, u64 pos)
+// bytes [pos, pos + 16) of the text as two little-endian words (text readable up to 24 bytes past pos)
+__device__ __forceinline__ void window128(const u64 *__restrict__ W, u64 pos, u64 &a, u64 &b)
 {
-    u64 q = pos >> 3; int sh = (int)(pos & 7) * 8;
-    u64 lo = W[q];
-    if (sh == 0) return lo;
-    u64 hi = W[q + 1];
-    return (lo >> sh) | (hi << (64 - sh));
+    const u64 q = pos >> 3; const int sh = (int)(pos & 7) * 8;
+    const u64 w0 = W[q], w1 = W[q + 1];
+    if (sh == 0) { a = w0; b = w1; return; }
+    const u64 w2 = W[q + 2];
+    a = (w0 >> sh) | (w1 << (64 - sh));
+    b = (w1 >> sh) | (w2 << (64 - sh));
+}
+// matching bytes at the start of two 16-byte windows (0..16)
+__device__ __forceinline__ u32 match16(u64 a0, u64 a1, u64 b0, u64 b1)
+{
+    const u64 x0 = a0 ^ b0, x1 = a1 ^ b1;
+    if (x0) return (u32)((__ffsll((long long)x0) - 1) >> 3);
+    if (x1) return 8u + (u32)((__ffsll((long long)x1) - 1) >> 3);
+    return 16u;
 }
 
+// one thread extends a match of l symbols between suffixes i and k (at most lim symbols can match)
 template <int SYM_BYTES>
-__global__ void __launch_bounds__(128)
-plcp_kernel(const void *__restrict__ Tv, u32 *__restrict__ PLCP, u64 n)
+__device__ __forceinline__ u64 extend_thread(const void *__restrict__ Tv, u64 i, u64 k, u64 l, u64 lim)
 {
-    u64 t = (u64)blockIdx.x * 128 + threadIdx.x;
-    u64 begin = t * kPlcpChunk;
-    if (begin >= n) return;
-    u64 end = begin + kPlcpChunk < n ? begin + kPlcpChunk : n;
-    u64 l = 0;
-    for (u64 i = begin; i < end; ++i) {
-        u64 k = PLCP[i];
-        if (k >= n) { l = 0; }
-        else {
-            u64 lim = n - (i > k ? i : k);               // symbols available to both suffixes
+    if (SYM_BYTES == 1) {
+        const u64 *W = (const u64 *)Tv;
+        while (l < lim) {
+            u64 a0, a1, b0, b1;
+            window128(W, i + l, a0, a1); window128(W, k + l, b0, b1);
+            const u32 m = match16(a0, a1, b0, b1);
+            l += m;
+            if (m < 16) break;
+        }
+    } else {
+        const u32 *S = (const u32 *)Tv;
+        while (l < lim && S[i + l] == S[k + l]) ++l;
+    }
+    return l < lim ? l : lim;
+}
+
+// the same by a whole warp: 512 bytes (32 symbols for integer texts) per step
+template <int SYM_BYTES>
+__device__ __forceinline__ u64 extend_warp(const void *__restrict__ Tv, u64 i, u64 k, u64 l, u64 lim, int lane)
+{
+    const int per = SYM_BYTES == 1 ? 16 : 1;
+    while (l < lim) {
+        const u64 off = l + (u64)lane * per;
+        const bool valid = off < lim;
+        u32 m = 0;
+        if (valid) {
             if (SYM_BYTES == 1) {
-                const u64 *W = (const u64 *)Tv;
-                while (l < lim) {
-                    u64 x = window64(W, i + l) ^ window64(W, k + l);
-                    if (x) { l += (u64)((__ffsll((long long)x) - 1) >> 3); break; }
-                    l += 8;
-                }
+                u64 a0, a1, b0, b1;
+                window128((const u64 *)Tv, i + off, a0, a1); window128((const u64 *)Tv, k + off, b0, b1);
+                m = match16(a0, a1, b0, b1);
             } else {
                 const u32 *S = (const u32 *)Tv;
-                while (l < lim && S[i + l] == S[k + l]) ++l;
+                m = S[i + off] == S[k + off] ? 1u : 0u;
             }
-            if (l > lim) l = lim;
         }
-        PLCP[i] = (u32)l;
-        if (l) --l;
+        const u32 stop = __ballot_sync(0xffffffffu, !valid || m < (u32)per);
+        if (stop == 0) { l += 32ull * per; continue; }
+        const int f = __ffs(stop) - 1;
+        const u32 mf = __shfl_sync(0xffffffffu, m, f);
+        l += (u64)f * per + mf;
+        break;
+    }
+    return l < lim ? l : lim;
+}
+
+// level kernel: warp w computes position i = first + w * stride from the bound PLCP[i - back] - back (back == 0: none)
+template <int SYM_BYTES>
+__global__ void __launch_bounds__(256)
+plcp_level_kernel(const void *__restrict__ Tv, u32 *__restrict__ PLCP, u64 n, u64 first, u64 stride, u64 back, u64 count)
+{
+    const int lane = threadIdx.x & 31;
+    const u64 w = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (w >= count) return;
+    const u64 i = first + w * stride;
+    if (i >= n) return;
+    const u64 k = PLCP[i];
+    u64 l = 0;
+    if (k < n) {
+        if (back) { const u64 pv = PLCP[i - back]; l = pv > back ? pv - back : 0; }
+        const u64 lim = n - (i > k ? i : k);
+        l = extend_warp<SYM_BYTES>(Tv, i, k, l < lim ? l : lim, lim, lane);
+    }
+    __syncwarp();
+    if (lane == 0) PLCP[i] = (u32)l;
+}
+
+// chunk kernel: thread t of the CTA walks positions [c0 + 32 t, c0 + 32 t + 32); the head of every chunk is final
+template <int SYM_BYTES>
+__global__ void __launch_bounds__(kPlcpThreads)
+plcp_chunk_kernel(const void *__restrict__ Tv, u32 *__restrict__ PLCP, u64 n)
+{
+    __shared__ u32 sh[kPlcpThreads * (kPlcpChunk + 1)];
+    const int tid = threadIdx.x;
+    const u64 c0 = (u64)blockIdx.x * (kPlcpThreads * kPlcpChunk);
+    for (int j = tid; j < kPlcpThreads * kPlcpChunk; j += kPlcpThreads) {
+        const u64 i = c0 + j;
+        sh[(j >> 5) * (kPlcpChunk + 1) + (j & 31)] = i < n ? PLCP[i] : 0u;
+    }
+    __syncthreads();
+    const u64 begin = c0 + (u64)tid * kPlcpChunk;
+    if (begin < n) {
+        u32 *mine = sh + tid * (kPlcpChunk + 1);
+        u64 l = mine[0];
+        const u64 end = begin + kPlcpChunk < n ? begin + kPlcpChunk : n;
+        for (u64 i = begin + 1; i < end; ++i) {
+            if (l) --l;
+            const u64 k = mine[i - begin];
+            if (k >= n) l = 0;
+            else {
+                const u64 lim = n - (i > k ? i : k);
+                l = extend_thread<SYM_BYTES>(Tv, i, k, l < lim ? l : lim, lim);
+            }
+            mine[i - begin] = (u32)l;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < kPlcpThreads * kPlcpChunk; j += kPlcpThreads) {
+        const u64 i = c0 + j;
+        if (i < n) PLCP[i] = sh[(j >> 5) * (kPlcpChunk + 1) + (j & 31)];
     }
 }
 
 size_t plcp_workspace_bytes(u64 n) { return (size_t)n * 8 + RadixSort<u32, u32>::temp_bytes(n) + 4096; }
+
+template <int SYM_BYTES>
+static void run_plcp_compare(Ctx &c, const void *d_T, u32 *d_PLCP, u64 n)
+{
+    const double per_level = 12.0;
+    // position 0 has no predecessor
+    LSC_LAUNCH(c, KC_PLCP, per_level, plcp_level_kernel<SYM_BYTES>, 1, 256, 0, d_T, d_PLCP, n, (u64)0, (u64)1, (u64)0, (u64)1);
+    if (n > (u64)kPlcpChunk) {
+        u64 s = kPlcpChunk;
+        while (s * 2 < n) s *= 2;                                  // largest chunk multiple 2^L < n
+        for (; s >= (u64)kPlcpChunk; s >>= 1) {
+            const u64 count = (n - 1 - s) / (2 * s) + 1;           // odd multiples of s below n
+            LSC_LAUNCH(c, KC_PLCP, (double)count * per_level, plcp_level_kernel<SYM_BYTES>, (u32)ceil_div(count * 32, 256), 256, 0,
+                       d_T, d_PLCP, n, s, 2 * s, s, count);
+        }
+    }
+    const double ab = (double)n * (SYM_BYTES == 1 ? 11.0 : 16.0);
+    LSC_LAUNCH(c, KC_PLCP, ab, plcp_chunk_kernel<SYM_BYTES>, (u32)ceil_div(n, (u64)kPlcpThreads * kPlcpChunk), kPlcpThreads, 0, d_T, d_PLCP, n);
+}
 
 int run_plcp(Ctx &c, const void *d_T, int sym_bytes, const u32 *d_SA, u32 *d_PLCP, u64 n)
 {
@@ -119,11 +231,8 @@ int run_plcp(Ctx &c, const void *d_T, int sym_bytes, const u32 *d_SA, u32 *d_PLC
         c.pass_class_override = -1;
         if (rc != 0) return -2;
     }
-    u64 threads = ceil_div(n, kPlcpChunk);
-    if (sym_bytes == 1)
-        LSC_LAUNCH(c, KC_PLCP, (double)n * 11, plcp_kernel<1>, (u32)ceil_div(threads, 128), 128, 0, d_T, d_PLCP, n);
-    else
-        LSC_LAUNCH(c, KC_PLCP, (double)n * 16, plcp_kernel<4>, (u32)ceil_div(threads, 128), 128, 0, d_T, d_PLCP, n);
+    if (sym_bytes == 1) run_plcp_compare<1>(c, d_T, d_PLCP, n);
+    else run_plcp_compare<4>(c, d_T, d_PLCP, n);
     return c.failed() ? -2 : 0;
 }
 

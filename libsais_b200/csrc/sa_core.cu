@@ -28,6 +28,7 @@
 #include "radix_sort.cuh"
 #include "scatter.cuh"
 #include "local_sort.cuh"
+#include "partition.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -668,7 +669,9 @@ size_t sa_workspace_bytes(u64 n, int sym_bytes)
                               + 4 + 4 + 4 + 4    /* a_pos, a_grp, a_slot x2 */
                               + 1);              /* lazy mode: separate small round buffers */
     size_t st = 3 * ceil_div(n, 32) * sizeof(u32) + ceil_div(n, kRankTile) * (kRankWarps + 1) * 3 * sizeof(u32) + 1024;
-    return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + 256 + 32 * 256 + 4096;
+    size_t msd = (size_t)(65536 + 65540 + 257) * 4 + 256 * 8 + (ceil_div(n, (u64)kPartTile) + 258) * kRadixSize * 8
+               + (ceil_div(n, 1536) + 2) * 4 + 8 * 256;     // round-0 MSD path: prefix histogram, offsets, tile status, tile table
+    return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + msd + 256 + 32 * 256 + 4096;
 }
 
 static int choose_key_symbols(u64 n, int b, double entropy_bits, int max_key_bits)
@@ -781,7 +784,59 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     bool fuse_keys = true;
     { const char *env = getenv("LIBSAIS_CUDA_FUSE_KEYS"); if (env && *env) fuse_keys = atoi(env) != 0; }
     int where;
-    if (fuse_keys) {
+    // ---- MSD path (partition.cuh): when the 16-bit key prefixes spread the suffixes over small buckets (random
+    // bytes, iid DNA: any near-uniform source), two UNSTABLE partition passes on the top 16 key bits and an
+    // in-shared-memory finish of every bucket replace the K/8 stable LSD passes.  Same sorted arrays.
+    bool msd = false;
+    u32 *m_boff = nullptr, *m_tstart = nullptr; u64 *m_base = nullptr; u64 m_maxb = 0, m_tiles2 = 0;
+    {
+        int mode = 1;
+        { const char *env = getenv("LIBSAIS_CUDA_MSD"); if (env && *env) mode = atoi(env); }
+        const u64 min_n = mode >= 2 ? 64 : ((u64)1 << 16);
+        if (fuse_keys && mode > 0 && (8 % b) == 0 && K >= 16 && n >= min_n) {
+            u32 *h16 = c.alloc_n<u32>(65536);
+            m_boff = c.alloc_n<u32>(65537 + 3); m_tstart = c.alloc_n<u32>(kRadixSize + 1); m_base = c.alloc_n<u64>(kRadixSize);
+            if (!h16 || !m_boff || !m_tstart || !m_base) return -2;
+            c.check(cudaMemsetAsync(h16, 0, 65536 * sizeof(u32), st));
+            const u64 nw = ceil_div(n * (u64)b, 64);
+            const u64 want = ceil_div(nw, kHist16Threads);
+            const u32 parts = (u32)(want < (u64)c.sm_count ? want : (u64)c.sm_count);
+            c.check(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHist16Bins * (int)sizeof(u32)));
+            LSC_LAUNCH(c, KC_SORT_HIST, (double)nw * 8, hist16_kernel, parts * kHist16Ranges, kHist16Threads, kHist16Bins * sizeof(u32), words, n, b, h16);
+            LSC_LAUNCH(c, KC_SORT_SCAN, 65536.0 * 8, scan16_kernel, 1, 1024, 0, h16, m_boff, m_base, m_tstart, c.d_scalars + S_MSD, (u32)kPartTile);
+            c.check(cudaMemcpyAsync(c.h_scalars + S_MSD, c.d_scalars + S_MSD, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            if (!c.sync()) return -2;
+            m_maxb = c.h_scalars[S_MSD]; m_tiles2 = c.h_scalars[S_MSD + 1];
+            msd = m_maxb <= (u64)kBucketMaxBucket;
+        }
+    }
+    if (msd) {
+        const u64 nt1 = ceil_div(n, (u64)kPartTile);
+        const u64 ntmax = nt1 > m_tiles2 ? nt1 : m_tiles2;
+        const size_t stw = n < (1ull << 30) ? sizeof(u32) : sizeof(u64);
+        void *status = c.alloc(ntmax * kRadixSize * stw);
+        u32 Cw = (u32)kBucketCap - (u32)m_maxb;
+        if (Cw > 6144) Cw = 6144;
+        const u64 btiles = ceil_div(n, (u64)Cw);
+        u32 *tb = c.alloc_n<u32>(btiles + 2);
+        if (!status || !tb) return -2;
+        u32 *tickets = (u32 *)(c.d_scalars + S_TICKET);
+        c.check(cudaMemsetAsync(tickets, 0, 8 * sizeof(u64), st));
+        KmerSrc src; src.words = words; src.nwords = nwords; src.text = bwt_mode ? (const u8 *)d_T : nullptr; src.n = n; src.b = b; src.K = K; src.key_shift = key_shift;
+        SegArgs seg; seg.boff = m_boff; seg.tstart = m_tstart;
+        c.check(cudaMemsetAsync(status, 0, nt1 * kRadixSize * stw, st));
+        launch_part_pass<u64, u32, KmerSrc, false>(c, KC_SORT_PASS_GEN, (double)n * (2.0 + 12.0), src, (const u64 *)nullptr, (const u32 *)nullptr, keyA, valA,
+                                                   n, nt1, key_shift + K - 8, 255u, m_base, seg, status, tickets, err);
+        c.check(cudaMemsetAsync(status, 0, m_tiles2 * kRadixSize * stw, st));
+        launch_part_pass<u64, u32, ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB,
+                                                   n, m_tiles2, key_shift + K - 16, 255u, (const u64 *)nullptr, seg, status, tickets + 1, err);
+        LSC_LAUNCH(c, KC_SORT_HIST, 0.0, bucket_tiles_kernel, (u32)ceil_div(btiles + 1, 256), 256, 0, m_boff, btiles, Cw, tb);
+        c.check(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
+        LSC_LAUNCH(c, KC_BUCKET_SORT, (double)n * 24.0, bucket_sort_kernel, (u32)btiles, kBucketThreads, sizeof(BucketSmem),
+                   keyB, valB, m_boff, tb, n, Cw, key_shift, K - 16, keyA, valA, err);
+        rs.passes = 2;
+        where = c.failed() ? -1 : 0;
+    } else if (fuse_keys) {
         KmerGen gen; gen.words = words; gen.text = bwt_mode ? (const u8 *)d_T : nullptr; gen.n = n; gen.b = b; gen.K = K; gen.key_shift = key_shift;
         // digit histograms straight from the s-gram histogram of the text when digits are symbol aligned
         bool hist_ready = false;

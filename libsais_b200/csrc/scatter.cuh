@@ -8,6 +8,7 @@
 // prefix-doubling rounds and for the phi array (reference compute_phi, src/libsais.c:8116-8142).
 #pragma once
 #include "radix_sort.cuh"
+#include "partition.cuh"
 
 namespace lsc {
 
@@ -66,10 +67,40 @@ static int partitioned_scatter(Ctx &c, const Gen &gen, u32 *ia, u32 *va, u32 *ib
     const int lo = bits > kRadixBits ? bits - kRadixBits : 0;
     const int saved_class = c.pass_class_override;
     const int kc = saved_class >= 0 ? saved_class : KC_SCATTER;
-    c.pass_class_override = kc;
-    int where = RadixSort<u32, u32>::template sort_from<Gen>(c, gen, ia, va, ib, vb, N, lo, bits, sort_temp, err, nullptr, hist_ready);
-    c.pass_class_override = saved_class;
-    if (where != 1) return -2;
+    static const bool stable_env = [] { const char *e = getenv("LIBSAIS_CUDA_SCATTER_STABLE"); return e && *e && atoi(e) != 0; }();
+    if (stable_env) {
+        c.pass_class_override = kc;
+        int where = RadixSort<u32, u32>::template sort_from<Gen>(c, gen, ia, va, ib, vb, N, lo, bits, sort_temp, err, nullptr, hist_ready);
+        c.pass_class_override = saved_class;
+        if (where != 1) return -2;
+    } else {
+        // order inside a window is irrelevant: the unstable partition pass (partition.cuh), same temp layout as the sort
+        char *t = (char *)sort_temp;
+        u64 *hist = (u64 *)t;               t += kMaxPasses * kRadixSize * sizeof(u64);
+        u64 *base = (u64 *)t;               t += kMaxPasses * kRadixSize * sizeof(u64);
+        u32 *tickets = (u32 *)t;            t += 256;
+        void *status = (void *)t;
+        const u64 nt = ceil_div(N, (u64)kPartTile);
+        const u32 dmask = (1u << (bits - lo)) - 1;
+        if (!hist_ready) {
+            c.check(cudaMemsetAsync(hist, 0, kRadixSize * sizeof(u64), c.stream));
+            SortPlan plan = make_sort_plan(lo, bits);
+            u64 want = ceil_div(N, (u64)512 * 8);
+            u32 grid = (u32)(want < (u64)c.sm_count * 4 ? (want ? want : 1) : (u64)c.sm_count * 4);
+            LSC_LAUNCH(c, kc, (double)N * 4.0, (sort_hist_kernel<u32, 512, Gen>), grid, 512, 0, ia, N, plan, hist, gen);
+        }
+        c.check(cudaMemsetAsync(tickets, 0, 256, c.stream));
+        LSC_LAUNCH(c, kc, 0.0, sort_scan_kernel, 1, kRadixSize, 0, hist, base);
+        c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * (N < (1ull << 30) ? sizeof(u32) : sizeof(u64)), c.stream));
+        const double ab = (double)N * ((Gen::kActive ? 2.0 : 8.0) + 8.0);
+        if constexpr (Gen::kActive) {
+            FuncSrc<Gen> src; src.f = gen;
+            launch_part_pass<u32, u32, FuncSrc<Gen>, false>(c, kc, ab, src, (const u32 *)nullptr, (const u32 *)nullptr, ib, vb, N, nt, lo, dmask, base, SegArgs(), status, tickets, err);
+        } else {
+            launch_part_pass<u32, u32, ArraySrc, false>(c, kc, ab, ArraySrc(), ia, va, ib, vb, N, nt, lo, dmask, base, SegArgs(), status, tickets, err);
+        }
+        if (c.failed()) return -2;
+    }
     LSC_LAUNCH(c, kc, (double)N * 12, scatter_pairs_kernel, (u32)ceil_div(N, 256), 256, 0, ib, vb, N, dst, dst_len);
     return c.failed() ? -2 : 0;
 }
