@@ -75,6 +75,18 @@ int64_t libsais_cuda_lcp_dev(const void * ctx, const uint32_t * d_PLCP, const ui
 /* Inverse BWT; mirrors libsais_unbwt() [:289]. */
 int64_t libsais_cuda_unbwt_dev(const void * ctx, const uint8_t * d_B, uint8_t * d_U, int64_t n, int64_t primary);
 
+/* ---- batch of independent BWT blocks over one or more GPUs (BASELINE config 4).
+ * HOST pointers (pinned memory lets the copies overlap; pageable buffers go through the pinned staging lanes).
+ * Block b is processed on devices[b % ndevices] (devices == NULL: the calling thread's current device); every
+ * device runs `lanes` host threads (0 = default 3) with one context each -- the reference's
+ * one-context-per-thread model [include/libsais.h:53-55] -- so one block's H2D copy, another's kernels and a
+ * third's D2H copy overlap.  primary[b] receives what libsais_bwt() returns for block b [include/libsais.h:182];
+ * device_ms (nullable) the device time of each block.  Returns 0, -1 (bad arguments) or -2 (a block failed). */
+int32_t libsais_cuda_bwt_batch(const uint8_t * const * T, uint8_t * const * U, const int32_t * n, int32_t * primary, float * device_ms,
+                               int32_t nblocks, const int32_t * devices, int32_t ndevices, int32_t lanes);
+/* Free the pooled contexts of libsais_cuda_bwt_batch (device workspaces, streams). */
+void    libsais_cuda_batch_release(void);
+
 /* ---- building blocks of the distributed prefix doubling (texts beyond one GPU's working set; orchestrated by
  * libsais_b200/dist.py: one process per GPU, torch.distributed / NCCL all-to-alls between these calls).
  * Device pointers; every call completes before it returns. */

@@ -9,6 +9,11 @@
 #include <cstring>
 #include <cstdlib>
 #include <new>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #define LIBSAIS_OPENMP 1      /* export the *_omp symbols unconditionally */
 #include "../../include/libsais.h"
@@ -37,7 +42,14 @@ Ctx *new_ctx(int device)
 
 struct DefaultCtx {
     Ctx *c = nullptr;
-    ~DefaultCtx() { if (c) { c->destroy(); delete c; c = nullptr; } }
+    // At process exit the CUDA runtime may already be unloading when thread-local destructors run: touching it
+    // then can fail or hang, so the context is simply leaked unless the runtime still answers.
+    ~DefaultCtx() {
+        if (!c) return;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) { c->destroy(); delete c; }
+        c = nullptr;
+    }
 };
 thread_local DefaultCtx tl_default;
 
@@ -112,11 +124,11 @@ template <typename IDX> u32 *upload_indexes(Ctx &c, const IDX *h_src, u64 count)
     u32 *d = c.alloc_n<u32>(count);
     if (!d) return nullptr;
     if (sizeof(IDX) == 4) {
-        copy_h2d(c, d, h_src, count * 4);
+        if (!copy_h2d(c, d, h_src, count * 4)) return nullptr;
     } else {
         i64 *wide = c.alloc_n<i64>(count);
         if (!wide) return nullptr;
-        copy_h2d(c, wide, h_src, count * 8);
+        if (!copy_h2d(c, wide, h_src, count * 8)) return nullptr;
         run_narrow(c, wide, d, count);
     }
     return d;
@@ -139,7 +151,7 @@ IDX sa_body(Ctx *c, const uint8_t *T, IDX *SA, IDX n, IDX fs, IDX *freq)
     SAResult res; SAOptions opt;
     if (build_sa(*c, d_T, 1, (u64)n, opt, &res) != 0) return -2;
     call.stop_timer();
-    download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
+    if (!download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch)) return -2;
     if (!call.finish()) return -2;
     store_freq(*c, freq);
     return 0;
@@ -161,7 +173,7 @@ IDX sa_int_body(Ctx *c, SYM *T, IDX *SA, IDX n, IDX k, IDX fs)
     SAResult res; SAOptions opt;
     if (build_sa(*c, d_T, (int)sizeof(SYM), (u64)n, opt, &res) != 0) return -2;
     call.stop_timer();
-    download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
+    if (!download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch)) return -2;
     if (!call.finish()) return -2;
     return 0;
 }
@@ -189,7 +201,7 @@ IDX gsa_body(Ctx *c, const uint8_t *T, IDX *SA, IDX n, IDX fs, IDX *freq)
     SAResult res; SAOptions opt;
     if (build_sa(*c, d_Tint, 4, (u64)n, opt, &res) != 0) return -2;
     call.stop_timer();
-    download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch);
+    if (!download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch)) return -2;
     if (!call.finish()) return -2;
     store_freq(*c, freq);
     return 0;
@@ -214,7 +226,7 @@ IDX plcp_gsa_body(Ctx *c, const uint8_t *T, const IDX *SA, IDX *PLCP, IDX n)
     if (!d_Tint) return -2;
     if (run_plcp(*c, d_Tint, 4, d_SA, d_P, (u64)n) != 0) return -2;
     call.stop_timer();
-    download_indexes<IDX>(*c, d_P, PLCP, (u64)n, wide);
+    if (!download_indexes<IDX>(*c, d_P, PLCP, (u64)n, wide)) return -2;
     if (!call.finish()) return -2;
     return 0;
 }
@@ -247,8 +259,8 @@ IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *f
     if (res.primary < 1 || res.primary > (u64)n) return -2;
     if (run_bwt_finish(*c, d_T, d_rows, d_U, (u64)n, res.primary) != 0) return -2;
     call.stop_timer();
-    copy_d2h(*c, U, d_U, (size_t)n);
-    if (n_aux) download_indexes<IDX>(*c, d_I, I, n_aux, res.scratch);
+    if (!copy_d2h(*c, U, d_U, (size_t)n)) return -2;
+    if (n_aux && !download_indexes<IDX>(*c, d_I, I, n_aux, res.scratch)) return -2;
     if (!call.finish()) return -2;
     store_freq(*c, freq);
     return aux ? 0 : (IDX)res.primary;
@@ -275,7 +287,7 @@ IDX unbwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, const IDX *f
     call.start_timer();
     if (run_unbwt(*c, d_B, d_U, (u64)n, (u64)I[0]) != 0) return -2;
     call.stop_timer();
-    copy_d2h(*c, U, d_U, (size_t)n);
+    if (!copy_d2h(*c, U, d_U, (size_t)n)) return -2;
     if (!call.finish()) return -2;
     return 0;
 }
@@ -297,7 +309,7 @@ IDX plcp_body(Ctx *c, const SYM *T, const IDX *SA, IDX *PLCP, IDX n)
     call.start_timer();
     if (run_plcp(*c, d_T, (int)sizeof(SYM), d_SA, d_P, (u64)n) != 0) return -2;
     call.stop_timer();
-    download_indexes<IDX>(*c, d_P, PLCP, (u64)n, wide);
+    if (!download_indexes<IDX>(*c, d_P, PLCP, (u64)n, wide)) return -2;
     if (!call.finish()) return -2;
     return 0;
 }
@@ -318,7 +330,7 @@ IDX lcp_body(Ctx *c, const IDX *PLCP, const IDX *SA, IDX *LCP, IDX n)
     call.start_timer();
     if (run_lcp(*c, d_P, d_SA, d_L, (u64)n) != 0) return -2;
     call.stop_timer();
-    download_indexes<IDX>(*c, d_L, LCP, (u64)n, wide);   // LCP may alias SA: SA was consumed above
+    if (!download_indexes<IDX>(*c, d_L, LCP, (u64)n, wide)) return -2;   // LCP may alias SA: SA was consumed above
     if (!call.finish()) return -2;
     return 0;
 }
@@ -589,6 +601,87 @@ int64_t libsais_cuda_unbwt_dev(const void *ctx, const uint8_t *d_B, uint8_t *d_U
     return call.finish() ? 0 : -2;
 }
 
+
+// ------------------------------------------------------------------ batch of independent blocks (BASELINE config 4)
+// The reference's model for many independent texts is "one context per host thread"
+// (include/libsais.h:53-55).  This is the same model packaged for GPUs: block b runs on
+// devices[b % ndevices]; every device gets `lanes` host threads with one context (= stream +
+// workspace) each, so the H2D copy of one block overlaps the kernels of another and the D2H of
+// a third -- both PCIe directions and the SMs stay busy.  Contexts live in a process-wide pool.
+namespace {
+std::mutex g_batch_mutex;
+std::map<int, std::vector<Ctx *>> g_batch_pool;
+
+Ctx *batch_ctx(int device, int lane)
+{
+    std::vector<Ctx *> &v = g_batch_pool[device];
+    while ((int)v.size() <= lane) v.push_back(nullptr);
+    if (!v[lane]) v[lane] = new_ctx(device);
+    return v[lane];
+}
+}  // namespace
+
+int32_t libsais_cuda_bwt_batch(const uint8_t *const *T, uint8_t *const *U, const int32_t *n, int32_t *primary, float *device_ms,
+                               int32_t nblocks, const int32_t *devices, int32_t ndevices, int32_t lanes)
+{
+    if (T == nullptr || U == nullptr || n == nullptr || primary == nullptr || nblocks < 0 || ndevices < 0 || lanes < 0) return -1;
+    if (nblocks == 0) return 0;
+    int ndev_all = libsais_cuda_device_count();
+    if (ndev_all <= 0) return -2;
+    std::vector<int> devs;
+    if (devices == nullptr || ndevices == 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return -2; }
+        devs.push_back(cur);
+    } else {
+        for (int i = 0; i < ndevices; ++i) { if (devices[i] < 0 || devices[i] >= ndev_all) return -1; devs.push_back(devices[i]); }
+    }
+    if (lanes == 0) lanes = 3;
+    if (lanes > 8) lanes = 8;
+    std::lock_guard<std::mutex> guard(g_batch_mutex);
+    const int D = (int)devs.size();
+    std::vector<Ctx *> ctxs((size_t)D * lanes, nullptr);
+    for (int d = 0; d < D; ++d)
+        for (int l = 0; l < lanes; ++l) {
+            // two entries of `devices` may name the same GPU: they get distinct lanes of that GPU's pool
+            int dup = 0;
+            for (int e = 0; e < d; ++e) if (devs[e] == devs[d]) ++dup;
+            Ctx *c = batch_ctx(devs[d], dup * lanes + l);
+            if (!c) return -2;
+            ctxs[(size_t)d * lanes + l] = c;
+        }
+    std::vector<std::atomic<int>> next(D);
+    for (int d = 0; d < D; ++d) next[d].store(0);
+    std::atomic<int> failed(0);
+    static int32_t dummy_A[4];
+    auto worker = [&](int d, int l) {
+        Ctx *c = ctxs[(size_t)d * lanes + l];
+        cudaSetDevice(c->device);
+        for (;;) {
+            const int j = next[d].fetch_add(1);
+            const long long b = (long long)d + (long long)j * D;
+            if (b >= nblocks) break;
+            const int32_t rc = bwt_body<int32_t>(c, T[b], U[b], dummy_A, n[b], 0, nullptr, 0, nullptr, false);
+            primary[b] = rc;
+            if (device_ms) device_ms[b] = c->last_device_ms;
+            if (rc < 0) failed.store(1);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int d = 0; d < D; ++d)
+        for (int l = 0; l < lanes; ++l) th.emplace_back(worker, d, l);
+    for (auto &t : th) t.join();
+    return failed.load() ? -2 : 0;
+}
+
+// Free the pooled contexts of the batch entry point (device workspaces, streams).
+void libsais_cuda_batch_release(void)
+{
+    std::lock_guard<std::mutex> guard(g_batch_mutex);
+    for (auto &kv : g_batch_pool)
+        for (Ctx *c : kv.second) if (c) { c->destroy(); delete c; }
+    g_batch_pool.clear();
+}
 
 // ------------------------------------------------------------------ distributed building blocks
 // (include/libsais_cuda.h; orchestrated by libsais_b200/dist.py with torch.distributed all-to-alls)

@@ -13,9 +13,9 @@ enum ScalarSlot {
     S_MAXSYM  = 259,   // max symbol of an integer text
     S_PRIMARY = 260,   // slot of suffix 0 (+1)
     S_BIGGRP  = 261,   // set when an unresolved group is larger than the local-sort tile
-    S_MSD     = 262,   // [262, 264): round-0 MSD path: largest 16-bit bucket, tiles of the segmented pass
     S_TICKET  = 264,   // [264, 272): tickets of the rank kernels (u32 views)
     S_MISC    = 272,   // [272, 304): LUT staging; [312, 320): debug counters
+    S_MSD     = 304,   // [304, 308): round-0 MSD path: largest 16-bit bucket, most tiles of a top-level bucket, overflow flag
     S_GSA_TOTAL = 320, // number of separators of a GSA text
     S_GSA_INVALID = 321, // set when the collection has an empty member (reference returns -1)
     S_ROUTE   = 384,   // [384, 449): per-destination counts of the distributed routing

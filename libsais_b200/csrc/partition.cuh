@@ -52,65 +52,80 @@ struct PartSmem {
     u32  cnt[kRadixSize];
     u32  tileoff[kRadixSize];
     u32  scan_tmp[32];
-    u32  tstart[kRadixSize + 1];           // segmented mode: first tile of every top-level bucket
     alignas(8) u64 mbar[2];
     u32  tile;
 };
 
-// Segmented mode (second MSD level): the input is the concatenation of 256 top-level buckets
-// [boff[c << 8], boff[(c + 1) << 8]); a tile is the intersection of a TILE-aligned cell of the array with one
-// bucket, so interior tiles stay full and 16-byte aligned (TMA) and every tile has ONE top-level digit c.
-// Its elements go to boff[c * 256 + d] + (elements with digit d in earlier tiles of the bucket) + rank.
-struct SegArgs { const u32 *boff; const u32 *tstart; };
+// Tickets are INTERLEAVED over independent segments: ticket t works on segment t % nseg, tile t / nseg of that
+// segment, and the chained scan of a tile only spans its own segment.  The predecessor of a tile was therefore
+// issued nseg tickets earlier -- with nseg >= the number of resident CTAs it has long finished, its INCLUSIVE
+// prefix is published, and the look-back ends after one (prefetched) status word instead of ~22 tiles and
+// several L2 round trips with spinning (profiles/part_pass_r2.md).
+//   segmented mode (second MSD level): segment = top-level bucket c = [boff[c << 8], boff[(c + 1) << 8]); a tile is
+//     the intersection of a TILE-aligned cell of the array with one bucket, so interior tiles stay full and
+//     16-byte aligned (TMA).  Elements go to boff[c * 256 + d] + (digit-d elements of earlier tiles of c) + rank.
+//   chunked mode (first level): segment = chunk of tpc consecutive tiles; cp[s][d] = digit-d elements in earlier
+//     chunks (from the per-chunk histograms hist16 takes anyway).  nseg == 1: plain chained scan over all tiles.
+struct PartArgs {
+    u64 n; int shift; u32 dmask;
+    const u64 *base;        // [256] global digit bases (not segmented)
+    const u32 *cp;          // [nseg][256] chunk prefixes, or null
+    u32 nseg, tpc;
+    const u32 *boff;        // segmented: [65537] offsets of the 16-bit buckets
+    const u32 *tstart;      // segmented: [257] exclusive scan of the tiles per top-level bucket
+    u32 *ticket; u32 *err; int use_bulk;
+};
 
-template <typename KeyT, typename ValT, int THREADS, int IPT, typename ST, typename Src, bool SEG>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : (THREADS <= 512 ? 2 : 1)))
+template <typename KeyT, typename ValT, int THREADS, int IPT, int MINB, typename ST, typename Src, bool SEG>
+__global__ void __launch_bounds__(THREADS, MINB)
 part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
-                 KeyT *__restrict__ kout, ValT *__restrict__ vout, u64 n,
-                 int shift, u32 dmask, const u64 *__restrict__ base, const SegArgs seg,
-                 ST *status, u32 *ticket, u32 *err, const Src src, const int use_bulk)
+                 KeyT *__restrict__ kout, ValT *__restrict__ vout, const PartArgs a, ST *status, const Src src)
 {
     typedef PartSmem<KeyT, ValT, THREADS, IPT> Smem;
     constexpr int TILE = THREADS * IPT;
-    static_assert(THREADS >= kRadixSize + 1 && THREADS % 32 == 0, "one thread per digit (+1) is assumed");
+    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one thread per digit is assumed");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shift = a.shift; const u32 dmask = a.dmask;
 
     if (tid == 0) {
-        sm.tile = atomicAdd(ticket, 1u);
+        sm.tile = atomicAdd(a.ticket, 1u);
         mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1);
         mbar_fence_init();
     }
     if (tid < kRadixSize) sm.cnt[tid] = 0;
-    if (SEG && tid <= kRadixSize) sm.tstart[tid] = seg.tstart[tid];
     __syncthreads();
-    const u32 tile = sm.tile;
+    const u32 ticket = sm.tile;
+    const u32 segi = ticket % a.nseg, j = ticket / a.nseg;           // segment, tile inside the segment
 
-    // ---- which elements: [lo, lo + count) of the input; look-back stops at tile `first`
-    u64 lo; u32 count, first = 0, bucket = 0;
+    // ---- which elements: [lo, lo + count) of the input
+    u64 lo; u32 count;
     if (SEG) {
-        if (tile >= sm.tstart[kRadixSize]) return;                 // grid is an upper bound
-        int a = 0, bnd = kRadixSize;                               // largest c with tstart[c] <= tile
-        while (bnd - a > 1) { const int mid = (a + bnd) >> 1; if (sm.tstart[mid] <= tile) a = mid; else bnd = mid; }
-        bucket = (u32)a; first = sm.tstart[a];
-        const u64 blo = seg.boff[(u32)a << 8], bhi = seg.boff[((u32)a + 1) << 8];
-        const u64 cell = blo / TILE + (tile - first);
+        const u32 t0 = a.tstart[segi], t1 = a.tstart[segi + 1];
+        if (j >= t1 - t0) return;                                     // grid = nseg * (most tiles of any bucket)
+        const u64 blo = a.boff[segi << 8], bhi = a.boff[(segi + 1) << 8];
+        const u64 cell = blo / TILE + j;
         const u64 clo = cell * TILE, chi = clo + TILE;
         lo = blo > clo ? blo : clo;
         count = (u32)((bhi < chi ? bhi : chi) - lo);
     } else {
-        lo = (u64)tile * TILE;
-        count = (u32)((n - lo) < (u64)TILE ? (n - lo) : (u64)TILE);
+        const u64 tile = (u64)segi * a.tpc + j;
+        lo = tile * TILE;
+        if (j >= a.tpc || lo >= a.n) return;
+        count = (u32)((a.n - lo) < (u64)TILE ? (a.n - lo) : (u64)TILE);
     }
     const bool full = count == (u32)TILE;
 
     // ---- load: element li of the tile is held by thread (li & 31) + 32 * warp-slot, warp-striped
     KeyT key[IPT];
     const u32 wbase = warp * (IPT * 32) + lane;
-    const bool bulk = Src::kMode == SRC_ARRAYS && full && use_bulk && ((lo * sizeof(ValT)) & 15) == 0 && ((lo * sizeof(KeyT)) & 15) == 0;
+    const bool bulk = Src::kMode == SRC_ARRAYS && full && a.use_bulk && ((lo * sizeof(ValT)) & 15) == 0 && ((lo * sizeof(KeyT)) & 15) == 0;
     u64 gbase = 0;
-    if (tid < kRadixSize) gbase = SEG ? (u64)seg.boff[(bucket << 8) + tid] : base[tid];
+    if (tid < kRadixSize) {
+        if (SEG) gbase = (u64)a.boff[(segi << 8) + tid];
+        else { gbase = a.base[tid]; if (a.cp != nullptr) gbase += (u64)a.cp[(u64)segi * kRadixSize + tid]; }
+    }
     if constexpr (Src::kMode == SRC_KMER) {
         // positions of the tile: p_hi down to p_lo; words [w_lo, w_lo + nw) cover bits [p_lo*b, p_hi*b + 64 + 63]
         const u64 p_hi = src.n - 1 - lo, p_lo = p_hi - (count - 1);
@@ -126,7 +141,7 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
         if (src.text != nullptr) {
             const u64 first_b = p_lo ? p_lo - 1 : 0;
             const uintptr_t a0 = ((uintptr_t)(src.text + first_b)) & ~(uintptr_t)3;
-            t0 = (u64)(a0 - (uintptr_t)src.text);                   // may wrap "below" the text by < 4 bytes: a0 is still inside the allocation's 256-B alignment
+            t0 = (u64)(a0 - (uintptr_t)src.text);                   // may wrap "below" the text by < 4 bytes: a0 is still inside the allocation's alignment
             const u32 nq = (u32)((p_hi + 3 - t0) >> 2);             // aligned 32-bit words that hold bytes [t0, p_hi - 1]
             const u32 *src32 = reinterpret_cast<const u32 *>(a0);
             u32 *sb32 = reinterpret_cast<u32 *>(sb);
@@ -190,14 +205,13 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     // ---- per digit: publish the tile count, prefetch the look-back, exclusive scan of the counts
     u32 cnt = 0, tileoff = 0;
     LookState<ST> ls;
+    const u32 nseg = a.nseg;
     if (tid < kRadixSize) {
         cnt = sm.cnt[tid];
-        st_relaxed(status + (u64)tile * kRadixSize + tid, tile == first ? StWord<ST>::inc(cnt) : StWord<ST>::agg(cnt));
+        st_relaxed(status + (u64)ticket * kRadixSize + tid, j == 0 ? StWord<ST>::inc(cnt) : StWord<ST>::agg(cnt));
 #pragma unroll
-        for (int j = 0; j < kLookBatch; ++j) {
-            const i64 idx = (i64)tile - 1 - j;
-            ls.w[j] = idx >= (i64)first ? ld_relaxed(status + (u64)idx * kRadixSize + tid) : StWord<ST>::inc(0);
-        }
+        for (int q = 0; q < kLookBatch; ++q)
+            ls.w[q] = (u32)(q + 1) <= j ? ld_relaxed(status + (u64)(ticket - (u32)(q + 1) * nseg) * kRadixSize + tid) : StWord<ST>::inc(0);
         u32 x = cnt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
@@ -234,29 +248,28 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
         }
     }
 
-    // ---- chained scan over the tiles of this segment
+    // ---- chained scan over the earlier tiles of this segment (tickets ticket - nseg, ticket - 2 nseg, ...)
     if (tid < kRadixSize) {
         u64 excl = 0;
-        if (tile != first) {
-            i64 look = (i64)tile - 1;
+        if (j != 0) {
             bool done = false;
 #pragma unroll
-            for (int j = 0; j < kLookBatch; ++j)
-                if (!done) done = lookback_consume<ST>(ls.w[j], status, look - j, (u32)tid, excl, err);
-            look -= kLookBatch;
+            for (int q = 0; q < kLookBatch; ++q)
+                if (!done) done = lookback_consume<ST>(ls.w[q], status, (i64)ticket - (i64)(q + 1) * nseg, (u32)tid, excl, a.err);
+            u32 back = kLookBatch;
             while (!done) {
                 ST w[kLookRefill];
 #pragma unroll
-                for (int j = 0; j < kLookRefill; ++j) {
-                    const i64 idx = look - j;
-                    w[j] = idx >= (i64)first ? ld_relaxed(status + (u64)idx * kRadixSize + tid) : StWord<ST>::inc(0);
+                for (int q = 0; q < kLookRefill; ++q) {
+                    const u32 k = back + 1 + q;
+                    w[q] = k <= j ? ld_relaxed(status + (u64)(ticket - k * nseg) * kRadixSize + tid) : StWord<ST>::inc(0);
                 }
 #pragma unroll
-                for (int j = 0; j < kLookRefill; ++j)
-                    if (!done) done = lookback_consume<ST>(w[j], status, look - j, (u32)tid, excl, err);
-                look -= kLookRefill;
+                for (int q = 0; q < kLookRefill; ++q)
+                    if (!done) done = lookback_consume<ST>(w[q], status, (i64)ticket - (i64)(back + 1 + q) * nseg, (u32)tid, excl, a.err);
+                back += kLookRefill;
             }
-            st_relaxed(status + (u64)tile * kRadixSize + tid, StWord<ST>::inc(excl + (u64)cnt));
+            st_relaxed(status + (u64)ticket * kRadixSize + tid, StWord<ST>::inc(excl + (u64)cnt));
         }
         sm.goff[tid] = gbase + excl - (u64)tileoff;
     }
@@ -275,81 +288,152 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     }
 }
 
-// Launch one partition pass.  `status` must hold (tiles + 1) * 256 words of ST, zeroed; `ticket` one zeroed u32.
-template <typename KeyT, typename ValT, typename Src, bool SEG>
-static void launch_part_pass(Ctx &c, int kc, double algo_bytes, const Src &src, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout,
-                             u64 n, u64 max_tiles, int shift, u32 dmask, const u64 *base, const SegArgs &seg,
-                             void *status, u32 *ticket, u32 *err)
+// Tile shapes of the partition pass; LIBSAIS_CUDA_PART_VARIANT selects one (profiles/part_pass_r2.md).
+struct PartVariant { int threads, ipt, minb; };
+static const PartVariant kPartVariants[] = { {384, 12, 2}, {384, 10, 3}, {512, 8, 2}, {256, 12, 4} };
+static const int kNumPartVariants = sizeof(kPartVariants) / sizeof(kPartVariants[0]);
+static inline int part_variant()
 {
-    constexpr int THREADS = 384, IPT = 12;
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LIBSAIS_CUDA_PART_VARIANT");
+        v = (e && *e) ? atoi(e) : 0;
+        if (v < 0 || v >= kNumPartVariants) v = 0;
+    }
+    return v;
+}
+static inline u32 part_tile() { const PartVariant &pv = kPartVariants[part_variant()]; return (u32)(pv.threads * pv.ipt); }
+
+template <typename KeyT, typename ValT, int THREADS, int IPT, int MINB, typename Src, bool SEG>
+static void launch_part_variant(Ctx &c, int kc, double algo_bytes, const Src &src, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout,
+                                PartArgs a, u64 grid, void *status)
+{
     typedef PartSmem<KeyT, ValT, THREADS, IPT> Smem;
     static const bool bulk_env = [] { const char *e = getenv("LIBSAIS_CUDA_TMA"); return !(e && *e && atoi(e) == 0); }();
-    const int use_bulk = bulk_env && Src::kMode == SRC_ARRAYS && (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0;
-    if (n < (1ull << 30)) {
-        auto kern = part_pass_kernel<KeyT, ValT, THREADS, IPT, u32, Src, SEG>;
+    a.use_bulk = bulk_env && Src::kMode == SRC_ARRAYS && (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0
+                 && ((size_t)THREADS * IPT * sizeof(KeyT)) % 16 == 0 && ((size_t)THREADS * IPT * sizeof(ValT)) % 16 == 0;
+    if (a.n < (1ull << 30)) {
+        auto kern = part_pass_kernel<KeyT, ValT, THREADS, IPT, MINB, u32, Src, SEG>;
         c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        LSC_LAUNCH(c, kc, algo_bytes, kern, (u32)max_tiles, THREADS, sizeof(Smem),
-                   kin, vin, kout, vout, n, shift, dmask, base, seg, (u32 *)status, ticket, err, src, use_bulk);
+        LSC_LAUNCH(c, kc, algo_bytes, kern, (u32)grid, THREADS, sizeof(Smem), kin, vin, kout, vout, a, (u32 *)status, src);
     } else {
-        auto kern = part_pass_kernel<KeyT, ValT, THREADS, IPT, u64, Src, SEG>;
+        auto kern = part_pass_kernel<KeyT, ValT, THREADS, IPT, MINB, u64, Src, SEG>;
         c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        LSC_LAUNCH(c, kc, algo_bytes, kern, (u32)max_tiles, THREADS, sizeof(Smem),
-                   kin, vin, kout, vout, n, shift, dmask, base, seg, (u64 *)status, ticket, err, src, use_bulk);
+        LSC_LAUNCH(c, kc, algo_bytes, kern, (u32)grid, THREADS, sizeof(Smem), kin, vin, kout, vout, a, (u64 *)status, src);
     }
 }
-static const int kPartTile = 384 * 12;
+
+// Launch one partition pass with `grid` tickets.  `status` must hold grid * 256 status words (u32 when
+// a.n < 2^30, else u64), zeroed; a.ticket one zeroed u32.
+template <typename KeyT, typename ValT, typename Src, bool SEG>
+static void launch_part_pass(Ctx &c, int kc, double algo_bytes, const Src &src, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout,
+                             const PartArgs &a, u64 grid, void *status)
+{
+    switch (part_variant()) {
+    case 1:  launch_part_variant<KeyT, ValT, 384, 10, 3, Src, SEG>(c, kc, algo_bytes, src, kin, vin, kout, vout, a, grid, status); break;
+    case 2:  launch_part_variant<KeyT, ValT, 512, 8, 2, Src, SEG>(c, kc, algo_bytes, src, kin, vin, kout, vout, a, grid, status); break;
+    case 3:  launch_part_variant<KeyT, ValT, 256, 12, 4, Src, SEG>(c, kc, algo_bytes, src, kin, vin, kout, vout, a, grid, status); break;
+    default: launch_part_variant<KeyT, ValT, 384, 12, 2, Src, SEG>(c, kc, algo_bytes, src, kin, vin, kout, vout, a, grid, status); break;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
-// hist16: histogram of the 16-bit prefixes of all n suffix keys, straight from the packed text (code width b
+// hist16: histogram of the 16-bit prefixes of all n suffix keys, straight from the packed text (code width B
 // divides 8, so a prefix is a whole number of symbols and every suffix's window starts on a symbol boundary).
-// 65536 u32 bins do not fit one CTA's shared memory: a CTA counts only the windows of ITS half of the bin
-// range (128 KB) over its share of the words; the two halves read the same words (L2 hits).
+// A CTA takes whole CHUNKS of the first partition pass (chunk s = elements [s * chunk_elems, ...) = a
+// contiguous range of text positions), counts them in shared memory with packed 16-bit counters (128 KB for all
+// 65536 bins), adds the chunk to the global histogram and stores the chunk's top-digit histogram H[s][256]
+// (-> chunk prefixes cp of the first pass).  A 16-bit counter that wraps changes the chunk's total: the flag
+// is set and the caller falls back to the stable LSD path (such a text is far too skewed for the MSD path anyway).
 // ---------------------------------------------------------------------------------------------
 static const int kHist16Threads = 1024;
-static const int kHist16Ranges = 2;
-static const int kHist16Bins = 65536 / kHist16Ranges;
+static const int kHist16Words = 32768;
 
+template <int B>
+__device__ __forceinline__ void hist16_add(u32 *sh, u64 hi, u64 lw, int i)
+{
+    const int off = i * B;
+    u32 win;
+    if (off <= 48) win = (u32)(hi >> (48 - off)) & 0xFFFFu;
+    else win = (u32)((hi << (off - 48)) | (lw >> (112 - off))) & 0xFFFFu;
+    atomicAdd(&sh[win >> 1], 1u << ((win & 1u) << 4));
+}
+
+template <int B>
 static __global__ void __launch_bounds__(kHist16Threads, 1)
-hist16_kernel(const u64 *__restrict__ words, u64 n, int b, u32 *__restrict__ hist)
+hist16_kernel(const u64 *__restrict__ words, u64 n, u32 *__restrict__ hist, u32 *__restrict__ H, u32 nchunks, u64 chunk_elems,
+              u64 *__restrict__ flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32 *sh = reinterpret_cast<u32 *>(smem_raw);
-    const int tid = threadIdx.x;
-    const u32 range = blockIdx.x % kHist16Ranges;
-    const u32 part = blockIdx.x / kHist16Ranges, nparts = gridDim.x / kHist16Ranges;
-    for (int i = tid; i < kHist16Bins; i += kHist16Threads) sh[i] = 0;
-    __syncthreads();
-    const int per = 64 / b;                                      // suffixes whose window starts in one word
-    const u64 nw = (n * (u64)b + 63) >> 6;
-    for (u64 w = (u64)part * kHist16Threads + tid; w < nw; w += (u64)nparts * kHist16Threads) {
-        const u64 hi = words[w], lw = words[w + 1];
-        const u64 q0 = w * (u64)per;
-        for (int i = 0; i < per; ++i) {
-            if (q0 + i >= n) break;
-            const int off = i * b;
-            const u64 x = off ? ((hi << off) | (lw >> (64 - off))) : hi;
-            const u32 win = (u32)(x >> 48);
-            if ((win >> 15) == range) atomicAdd(&sh[win & (kHist16Bins - 1)], 1u);
+    __shared__ u32 s_red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int PER = 64 / B;                                    // suffixes whose window starts in one word
+    for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(sh);
+            for (int i = tid; i < kHist16Words / 4; i += kHist16Threads) z[i] = make_uint4(0, 0, 0, 0);
         }
-    }
-    __syncthreads();
-    for (int i = tid; i < kHist16Bins; i += kHist16Threads) {
-        const u32 v = sh[i];
-        if (v) atomicAdd(&hist[range * kHist16Bins + i], v);
+        __syncthreads();
+        const u64 e0 = (u64)chunk * chunk_elems;
+        const u64 e1 = e0 + chunk_elems < n ? e0 + chunk_elems : n;
+        const u64 p_lo = n - e1, p_hi = n - 1 - e0;                // positions of the chunk, inclusive
+        const u64 w_first = (p_lo * B) >> 6, w_last = (p_hi * B) >> 6;
+        for (u64 w = w_first + tid; w <= w_last; w += kHist16Threads) {
+            const u64 hi = words[w], lw = words[w + 1];
+            const u64 q0 = w * PER;
+            if (q0 >= p_lo && q0 + (PER - 1) <= p_hi) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) hist16_add<B>(sh, hi, lw, i);
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < PER; ++i) if (q0 + i >= p_lo && q0 + i <= p_hi) hist16_add<B>(sh, hi, lw, i);
+            }
+        }
+        __syncthreads();
+        // flush + check the total
+        u32 total = 0;
+        for (int i = tid; i < kHist16Words; i += kHist16Threads) {
+            const u32 v = sh[i];
+            if (v) {
+                const u32 lo16 = v & 0xFFFFu, hi16 = v >> 16;
+                if (lo16) atomicAdd(&hist[2 * i], lo16);
+                if (hi16) atomicAdd(&hist[2 * i + 1], hi16);
+                total += lo16 + hi16;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+        if (lane == 0) s_red[warp] = total;
+        // top-digit histogram of the chunk: digit d = bins [256 d, 256 d + 256) = words [128 d, 128 d + 128)
+        if (tid < kRadixSize) {
+            u32 sum = 0;
+            for (int k = 0; k < 128; ++k) { const u32 v = sh[tid * 128 + ((k + tid) & 127)]; sum += (v & 0xFFFFu) + (v >> 16); }
+            H[(u64)chunk * kRadixSize + tid] = sum;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            u32 t = 0;
+            for (int w = 0; w < kHist16Threads / 32; ++w) t += s_red[w];
+            if ((u64)t != e1 - e0) *flag = 1;
+        }
+        __syncthreads();
     }
 }
 
 // One CTA: boff[0..65536] = exclusive scan of hist16 (boff[65536] = n), base256[c] = boff[c << 8] (u64, the digit
-// bases of the first partition pass), tstart[0..256] = first tile of every top-level bucket in the segmented
-// pass, out[0] = largest bucket, out[1] = number of tiles of the segmented pass.
+// bases of the first partition pass), tstart[0..256] = exclusive scan of the tiles per top-level bucket of the
+// segmented pass, cp[s][d] = exclusive scan over the chunks of H[s][d] (in place), out[0] = largest bucket,
+// out[1] = most tiles of any top-level bucket.
 static __global__ void __launch_bounds__(1024)
 scan16_kernel(const u32 *__restrict__ hist, u32 *__restrict__ boff, u64 *__restrict__ base256, u32 *__restrict__ tstart,
-              u64 *__restrict__ out, u32 tile)
+              u32 *__restrict__ H, u32 nchunks, u64 *__restrict__ out, u32 tile)
 {
     __shared__ u32 s_tot[32];
     __shared__ u32 s_max[32];
     __shared__ u32 s_b[kRadixSize + 1];
     __shared__ u32 s_w[8];
+    __shared__ u32 s_m[8];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint4 *h4 = reinterpret_cast<const uint4 *>(hist + t * 64);        // thread t owns bins [64t, 64t + 64)
     u32 sum = 0, mx = 0;
@@ -399,17 +483,28 @@ scan16_kernel(const u32 *__restrict__ hist, u32 *__restrict__ boff, u64 *__restr
     if (t < kRadixSize) {
         const u32 lo = s_b[t], hi = s_b[t + 1];
         nt = hi > lo ? (hi - 1) / tile - lo / tile + 1 : 0;
-        u32 x = nt;
+        u32 x = nt, m = nt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += o; }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { u32 o = __shfl_xor_sync(0xffffffffu, m, off); m = o > m ? o : m; }
         if (lane == 31) s_w[warp] = x;
+        if (lane == 0) s_m[warp] = m;
         ex = x - nt;
+        // chunk prefixes of digit t
+        u32 run = 0;
+        for (u32 s = 0; s < nchunks; ++s) { const u32 v = H[(u64)s * kRadixSize + t]; H[(u64)s * kRadixSize + t] = run; run += v; }
     }
     __syncthreads();
     if (t < kRadixSize) {
         for (int w = 0; w < warp; ++w) ex += s_w[w];
         tstart[t] = ex;
-        if (t == kRadixSize - 1) { tstart[kRadixSize] = ex + nt; out[1] = ex + nt; }
+        if (t == kRadixSize - 1) {
+            tstart[kRadixSize] = ex + nt;
+            u32 m = 0;
+            for (int w = 0; w < 8; ++w) m = s_m[w] > m ? s_m[w] : m;
+            out[1] = m;
+        }
     }
 }
 
@@ -425,16 +520,22 @@ scan16_kernel(const u32 *__restrict__ hist, u32 *__restrict__ boff, u64 *__restr
 //      (unordered), 4. every element counts the members of its bin that precede it (bins hold ~1 element
 //      for uniform keys) and writes itself to its final slot -- a warp's 32 elements land in (nearly) the
 //      same 32 consecutive slots, so the global stores coalesce without another staging step.
+// When the tile's key range fits 32 bits (always, for the texts this path accepts in practice) an element is
+// ONE 64-bit word in shared memory, (k-mer - first k-mer of the tile) << 32 | ~position: its bin is a shift,
+// the order is an integer compare, and the first 8 elements of a thread stay in registers between steps 1 and 3
+// (the others are re-read from global memory: L2 hits).  The preceding text byte of BWT calls rides in a byte
+// array.  Wider ranges take the generic path (u64 key + u32 position per element).
 // ---------------------------------------------------------------------------------------------
 static const int kBucketCap = 7680;
 static const int kBucketThreads = 512;
 static const int kBucketBins = 8192;             // packed two per 32-bit word
 static const int kBucketBinBits = 13;
+static const int kBucketKeep = 8;                // elements of a thread kept in registers between steps 1 and 3
 static const u32 kBucketMaxBucket = kBucketCap - 1536;     // largest 16-bit bucket the path accepts (window >= 1536)
 
 struct BucketSmem {
-    u64 keys[kBucketCap];
-    u32 pos[kBucketCap];
+    u64 keys[kBucketCap];                        // compact path: composite words
+    u32 pos[kBucketCap];                         // compact path: preceding bytes (u8 view)
     u32 bins[kBucketBins / 2];
     u32 scan_tmp[32];
 };
@@ -455,6 +556,42 @@ bucket_tiles_kernel(const u32 *__restrict__ boff, u64 ntiles, u32 C, u32 *__rest
     if (j <= ntiles) tb[j] = lower_bound_u32(boff, 0, 65536, j * (u64)C);
 }
 
+// exclusive scan of the packed 16-bit bin counters (8192 bins, thread t owns words [8t, 8t + 8)); afterwards the
+// low / high half of a word is the first slot of its bin.  All threads of the CTA call it.
+__device__ __forceinline__ void bucket_scan_bins(BucketSmem &sm, int tid, int lane, int warp)
+{
+    u32 w[8]; u32 sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { w[i] = sm.bins[tid * 8 + i]; sum += (w[i] & 0xFFFFu) + (w[i] >> 16); }
+    u32 inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
+    if (lane == 31) sm.scan_tmp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 x = lane < kBucketThreads / 32 ? sm.scan_tmp[lane] : 0, y = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, y, off); if (lane >= off) y += o; }
+        sm.scan_tmp[lane] = y - x;
+    }
+    __syncthreads();
+    u32 run = sm.scan_tmp[warp] + inc - sum;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const u32 a = w[i] & 0xFFFFu, bq = w[i] >> 16;
+        sm.bins[tid * 8 + i] = run | ((run + a) << 16);
+        run += a + bq;
+    }
+    __syncthreads();
+}
+// after step 3 a bin's counter is its END; its begin is the end of the bin before
+__device__ __forceinline__ void bucket_bin_range(const BucketSmem &sm, u32 bin, u32 &beg, u32 &end)
+{
+    const u32 wv = sm.bins[bin >> 1];
+    end = (bin & 1) ? (wv >> 16) : (wv & 0xFFFFu);
+    beg = bin == 0 ? 0u : ((bin & 1) ? (wv & 0xFFFFu) : (sm.bins[(bin >> 1) - 1] >> 16));
+}
+
 static __global__ void __launch_bounds__(kBucketThreads, 2)
 bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, const u32 *__restrict__ boff, const u32 *__restrict__ tb,
                    u64 n, u32 C, int key_shift, int R,             // R = K - 16: k-mer bits below the bucket prefix
@@ -469,46 +606,89 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
     if (cnt == 0) return;
     if (cnt > (u32)kBucketCap) { if (tid == 0) *err = 3; return; }  // a bucket larger than promised
     const u32 nb = B1 - B0;
-    const int sh_raw = R + (nb > 1 ? 32 - __clz(nb - 1) : 0) - kBucketBinBits;
-    const int sh = sh_raw > 0 ? sh_raw : 0;
+    const int span_bits = R + (nb > 1 ? 32 - __clz(nb - 1) : 0);     // (k-mer - kbase) < 2^span_bits
+    const int sh = span_bits > kBucketBinBits ? span_bits - kBucketBinBits : 0;
     const u64 kbase = (u64)B0 << R;
+    const u64 lowmask = ((u64)1 << key_shift) - 1;
 
     for (int i = tid; i < kBucketBins / 2; i += kBucketThreads) sm.bins[i] = 0;
     __syncthreads();
-    // 1. histogram
+
+    if (span_bits <= 32) {
+        // ---- compact path
+        u8 *prevb = reinterpret_cast<u8 *>(sm.pos);
+        const int csh = 32 + sh;
+        u64 keep[kBucketKeep]; u32 keepb = 0, keepb2 = 0;
+        // 1. histogram (first kBucketKeep elements of the thread stay in registers)
+#pragma unroll
+        for (int q = 0; q < kBucketKeep; ++q) {
+            const u32 i = q * kBucketThreads + tid;
+            keep[q] = 0;
+            if (i < cnt) {
+                const u64 key = kin[s + i];
+                const u32 p = vin[s + i];
+                const u64 comp = (((key >> key_shift) - kbase) << 32) | (u64)(~p);
+                keep[q] = comp;
+                if (q < 4) keepb |= (u32)(key & lowmask) << (8 * q); else keepb2 |= (u32)(key & lowmask) << (8 * (q - 4));
+                const u32 bin = min((u32)(comp >> csh), (u32)kBucketBins - 1);
+                atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
+            }
+        }
+        for (u32 i = kBucketKeep * kBucketThreads + tid; i < cnt; i += kBucketThreads) {
+            const u64 rel = (kin[s + i] >> key_shift) - kbase;
+            const u32 bin = min((u32)(rel >> sh), (u32)kBucketBins - 1);
+            atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
+        }
+        __syncthreads();
+        // 2. exclusive scan
+        bucket_scan_bins(sm, tid, lane, warp);
+        // 3. drop every element into its bin (the bin's counter becomes its end)
+#pragma unroll
+        for (int q = 0; q < kBucketKeep; ++q) {
+            const u32 i = q * kBucketThreads + tid;
+            if (i < cnt) {
+                const u64 comp = keep[q];
+                const u32 bin = min((u32)(comp >> csh), (u32)kBucketBins - 1);
+                const u32 old = atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
+                const u32 slot = (old >> ((bin & 1) * 16)) & 0xFFFFu;
+                sm.keys[slot] = comp;
+                prevb[slot] = (u8)((q < 4 ? keepb >> (8 * q) : keepb2 >> (8 * (q - 4))) & 255u);
+            }
+        }
+        for (u32 i = kBucketKeep * kBucketThreads + tid; i < cnt; i += kBucketThreads) {
+            const u64 key = kin[s + i];
+            const u32 p = vin[s + i];
+            const u64 comp = (((key >> key_shift) - kbase) << 32) | (u64)(~p);
+            const u32 bin = min((u32)(comp >> csh), (u32)kBucketBins - 1);
+            const u32 old = atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
+            const u32 slot = (old >> ((bin & 1) * 16)) & 0xFFFFu;
+            sm.keys[slot] = comp;
+            prevb[slot] = (u8)(key & lowmask);
+        }
+        __syncthreads();
+        // 4. rank inside the bin (composite words are distinct: the positions are), write to the final slot
+        for (u32 i = tid; i < cnt; i += kBucketThreads) {
+            const u64 comp = sm.keys[i];
+            const u32 bin = min((u32)(comp >> csh), (u32)kBucketBins - 1);
+            u32 beg, end;
+            bucket_bin_range(sm, bin, beg, end);
+            u32 r = 0;
+            for (u32 q = beg; q < end; ++q) r += sm.keys[q] < comp ? 1u : 0u;
+            const u64 o = s + beg + r;
+            kout[o] = (((comp >> 32) + kbase) << key_shift) | (u64)prevb[i];
+            vout[o] = ~(u32)comp;
+        }
+        return;
+    }
+
+    // ---- generic path: u64 key + u32 position per element
     for (u32 i = tid; i < cnt; i += kBucketThreads) {
         const u64 km = kin[s + i] >> key_shift;
         const u32 bin = min((u32)((km - kbase) >> sh), (u32)kBucketBins - 1);
         atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
     }
     __syncthreads();
-    // 2. exclusive scan over the 8192 bins: thread t owns words [8t, 8t + 8)
-    {
-        u32 w[8]; u32 sum = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { w[i] = sm.bins[tid * 8 + i]; sum += (w[i] & 0xFFFFu) + (w[i] >> 16); }
-        u32 inc = sum;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
-        if (lane == 31) sm.scan_tmp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            u32 x = lane < kBucketThreads / 32 ? sm.scan_tmp[lane] : 0, y = x;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, y, off); if (lane >= off) y += o; }
-            sm.scan_tmp[lane] = y - x;
-        }
-        __syncthreads();
-        u32 run = sm.scan_tmp[warp] + inc - sum;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const u32 a = w[i] & 0xFFFFu, bq = w[i] >> 16;
-            sm.bins[tid * 8 + i] = run | ((run + a) << 16);
-            run += a + bq;
-        }
-    }
-    __syncthreads();
-    // 3. drop every element into its bin (the bin's counter becomes its end)
+    bucket_scan_bins(sm, tid, lane, warp);
     for (u32 i = tid; i < cnt; i += kBucketThreads) {
         const u64 key = kin[s + i];
         const u32 p = vin[s + i];
@@ -519,18 +699,16 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
         sm.pos[slot] = p;
     }
     __syncthreads();
-    // 4. rank inside the bin, write to the final slot
     for (u32 i = tid; i < cnt; i += kBucketThreads) {
         const u64 key = sm.keys[i], km = key >> key_shift;
         const u32 p = sm.pos[i];
         const u32 bin = min((u32)((km - kbase) >> sh), (u32)kBucketBins - 1);
-        const u32 wv = sm.bins[bin >> 1];
-        const u32 end = (bin & 1) ? (wv >> 16) : (wv & 0xFFFFu);
-        const u32 beg = bin == 0 ? 0u : ((bin & 1) ? (wv & 0xFFFFu) : (sm.bins[(bin >> 1) - 1] >> 16));
+        u32 beg, end;
+        bucket_bin_range(sm, bin, beg, end);
         u32 r = 0;
-        for (u32 j = beg; j < end; ++j) {
-            const u64 kj = sm.keys[j] >> key_shift;
-            r += (kj < km || (kj == km && sm.pos[j] > p)) ? 1u : 0u;
+        for (u32 q = beg; q < end; ++q) {
+            const u64 kj = sm.keys[q] >> key_shift;
+            r += (kj < km || (kj == km && sm.pos[q] > p)) ? 1u : 0u;
         }
         const u64 o = s + beg + r;
         kout[o] = key;

@@ -669,8 +669,8 @@ size_t sa_workspace_bytes(u64 n, int sym_bytes)
                               + 4 + 4 + 4 + 4    /* a_pos, a_grp, a_slot x2 */
                               + 1);              /* lazy mode: separate small round buffers */
     size_t st = 3 * ceil_div(n, 32) * sizeof(u32) + ceil_div(n, kRankTile) * (kRankWarps + 1) * 3 * sizeof(u32) + 1024;
-    size_t msd = (size_t)(65536 + 65540 + 257) * 4 + 256 * 8 + (ceil_div(n, (u64)kPartTile) + 258) * kRadixSize * 8
-               + (ceil_div(n, 1536) + 2) * 4 + 8 * 256;     // round-0 MSD path: prefix histogram, offsets, tile status, tile table
+    size_t msd = (size_t)(65536 + 65540 + 257 + 1024 * 256) * 4 + 256 * 8 + (ceil_div(n, 3072) + 2048) * kRadixSize * 8
+               + (ceil_div(n, 1536) + 2) * 4 + 10 * 256;    // round-0 MSD path: prefix histogram, offsets, chunk prefixes, tile status, tile table
     return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + msd + 256 + 32 * 256 + 4096;
 }
 
@@ -788,7 +788,15 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     // bytes, iid DNA: any near-uniform source), two UNSTABLE partition passes on the top 16 key bits and an
     // in-shared-memory finish of every bucket replace the K/8 stable LSD passes.  Same sorted arrays.
     bool msd = false;
-    u32 *m_boff = nullptr, *m_tstart = nullptr; u64 *m_base = nullptr; u64 m_maxb = 0, m_tiles2 = 0;
+    u32 *m_boff = nullptr, *m_tstart = nullptr, *m_H = nullptr; u64 *m_base = nullptr; u64 m_maxb = 0, m_maxnt = 0;
+    const u32 ptile = part_tile();
+    const u64 nt1 = ceil_div(n, (u64)ptile);
+    u64 want_seg = (u64)c.sm_count * 2;                                             // chunks of the first pass
+    { const char *env = getenv("LIBSAIS_CUDA_PART_NSEG"); if (env && *env && atoi(env) > 0) want_seg = (u64)atoi(env); }
+    if (want_seg > 1024) want_seg = 1024;
+    u32 nseg1 = (u32)(nt1 < want_seg ? nt1 : want_seg);
+    const u32 tpc = (u32)ceil_div(nt1, (u64)nseg1);
+    nseg1 = (u32)ceil_div(nt1, (u64)tpc);
     {
         int mode = 1;
         { const char *env = getenv("LIBSAIS_CUDA_MSD"); if (env && *env) mode = atoi(env); }
@@ -796,25 +804,35 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         if (fuse_keys && mode > 0 && (8 % b) == 0 && K >= 16 && n >= min_n) {
             u32 *h16 = c.alloc_n<u32>(65536);
             m_boff = c.alloc_n<u32>(65537 + 3); m_tstart = c.alloc_n<u32>(kRadixSize + 1); m_base = c.alloc_n<u64>(kRadixSize);
-            if (!h16 || !m_boff || !m_tstart || !m_base) return -2;
+            m_H = c.alloc_n<u32>((size_t)nseg1 * kRadixSize);
+            if (!h16 || !m_boff || !m_tstart || !m_base || !m_H) return -2;
             c.check(cudaMemsetAsync(h16, 0, 65536 * sizeof(u32), st));
-            const u64 nw = ceil_div(n * (u64)b, 64);
-            const u64 want = ceil_div(nw, kHist16Threads);
-            const u32 parts = (u32)(want < (u64)c.sm_count ? want : (u64)c.sm_count);
-            c.check(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHist16Bins * (int)sizeof(u32)));
-            LSC_LAUNCH(c, KC_SORT_HIST, (double)nw * 8, hist16_kernel, parts * kHist16Ranges, kHist16Threads, kHist16Bins * sizeof(u32), words, n, b, h16);
-            LSC_LAUNCH(c, KC_SORT_SCAN, 65536.0 * 8, scan16_kernel, 1, 1024, 0, h16, m_boff, m_base, m_tstart, c.d_scalars + S_MSD, (u32)kPartTile);
-            c.check(cudaMemcpyAsync(c.h_scalars + S_MSD, c.d_scalars + S_MSD, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            c.check(cudaMemsetAsync(c.d_scalars + S_MSD, 0, 4 * sizeof(u64), st));
+            const u32 grid = nseg1 < (u32)c.sm_count ? nseg1 : (u32)c.sm_count;
+            const u64 chunk_elems = (u64)tpc * ptile;
+            const size_t hsm = kHist16Words * sizeof(u32);
+            const double hb = (double)ceil_div(n * (u64)b, 64) * 8;
+            u64 *flag = c.d_scalars + S_MSD + 2;
+            if (b == 8)      { c.check(cudaFuncSetAttribute(hist16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<8>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+            else if (b == 4) { c.check(cudaFuncSetAttribute(hist16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<4>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+            else if (b == 2) { c.check(cudaFuncSetAttribute(hist16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<2>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+            else             { c.check(cudaFuncSetAttribute(hist16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<1>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+            LSC_LAUNCH(c, KC_SORT_SCAN, 65536.0 * 8, scan16_kernel, 1, 1024, 0, h16, m_boff, m_base, m_tstart, m_H, nseg1, c.d_scalars + S_MSD, ptile);
+            c.check(cudaMemcpyAsync(c.h_scalars + S_MSD, c.d_scalars + S_MSD, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
             if (!c.sync()) return -2;
-            m_maxb = c.h_scalars[S_MSD]; m_tiles2 = c.h_scalars[S_MSD + 1];
-            msd = m_maxb <= (u64)kBucketMaxBucket;
+            m_maxb = c.h_scalars[S_MSD]; m_maxnt = c.h_scalars[S_MSD + 1];
+            msd = c.h_scalars[S_MSD + 2] == 0 && m_maxb <= (u64)kBucketMaxBucket;
         }
     }
     if (msd) {
-        const u64 nt1 = ceil_div(n, (u64)kPartTile);
-        const u64 ntmax = nt1 > m_tiles2 ? nt1 : m_tiles2;
+        const u64 grid1 = (u64)nseg1 * tpc, grid2 = (u64)kRadixSize * m_maxnt;
+        const u64 gmax = grid1 > grid2 ? grid1 : grid2;
         const size_t stw = n < (1ull << 30) ? sizeof(u32) : sizeof(u64);
-        void *status = c.alloc(ntmax * kRadixSize * stw);
+        void *status = c.alloc(gmax * kRadixSize * stw);
         u32 Cw = (u32)kBucketCap - (u32)m_maxb;
         if (Cw > 6144) Cw = 6144;
         const u64 btiles = ceil_div(n, (u64)Cw);
@@ -823,13 +841,13 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         u32 *tickets = (u32 *)(c.d_scalars + S_TICKET);
         c.check(cudaMemsetAsync(tickets, 0, 8 * sizeof(u64), st));
         KmerSrc src; src.words = words; src.nwords = nwords; src.text = bwt_mode ? (const u8 *)d_T : nullptr; src.n = n; src.b = b; src.K = K; src.key_shift = key_shift;
-        SegArgs seg; seg.boff = m_boff; seg.tstart = m_tstart;
-        c.check(cudaMemsetAsync(status, 0, nt1 * kRadixSize * stw, st));
-        launch_part_pass<u64, u32, KmerSrc, false>(c, KC_SORT_PASS_GEN, (double)n * (2.0 + 12.0), src, (const u64 *)nullptr, (const u32 *)nullptr, keyA, valA,
-                                                   n, nt1, key_shift + K - 8, 255u, m_base, seg, status, tickets, err);
-        c.check(cudaMemsetAsync(status, 0, m_tiles2 * kRadixSize * stw, st));
-        launch_part_pass<u64, u32, ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB,
-                                                   n, m_tiles2, key_shift + K - 16, 255u, (const u64 *)nullptr, seg, status, tickets + 1, err);
+        PartArgs pa; pa.n = n; pa.dmask = 255u; pa.err = err; pa.use_bulk = 0;
+        pa.shift = key_shift + K - 8; pa.base = m_base; pa.cp = m_H; pa.nseg = nseg1; pa.tpc = tpc; pa.boff = nullptr; pa.tstart = nullptr; pa.ticket = tickets;
+        c.check(cudaMemsetAsync(status, 0, grid1 * kRadixSize * stw, st));
+        launch_part_pass<u64, u32, KmerSrc, false>(c, KC_SORT_PASS_GEN, (double)n * (2.0 + 12.0), src, (const u64 *)nullptr, (const u32 *)nullptr, keyA, valA, pa, grid1, status);
+        pa.shift = key_shift + K - 16; pa.base = nullptr; pa.cp = nullptr; pa.nseg = kRadixSize; pa.tpc = 0; pa.boff = m_boff; pa.tstart = m_tstart; pa.ticket = tickets + 1;
+        c.check(cudaMemsetAsync(status, 0, grid2 * kRadixSize * stw, st));
+        launch_part_pass<u64, u32, ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
         LSC_LAUNCH(c, KC_SORT_HIST, 0.0, bucket_tiles_kernel, (u32)ceil_div(btiles + 1, 256), 256, 0, m_boff, btiles, Cw, tb);
         c.check(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
         LSC_LAUNCH(c, KC_BUCKET_SORT, (double)n * 24.0, bucket_sort_kernel, (u32)btiles, kBucketThreads, sizeof(BucketSmem),
@@ -1244,8 +1262,8 @@ size_t route_workspace_bytes(u64 count) { return (size_t)count * (8 + 8 + 4) + R
 int run_route(Ctx &c, const u32 *d_a, const u32 *d_b, u64 count, u64 add, u64 limit, u64 block, u32 world,
               u32 *d_a_out, u32 *d_b_out, u64 *counts_out)
 {
+    if (world == 0 || world > kRouteMaxRanks) return -1;        // before touching counts_out: callers size it for <= 64 ranks
     for (u32 r = 0; r < world; ++r) counts_out[r] = 0;
-    if (world == 0 || world > kRouteMaxRanks) return -1;
     if (count == 0) return 0;
     u64 *keyA = c.alloc_n<u64>(count), *keyB = c.alloc_n<u64>(count);
     u32 *valA = c.alloc_n<u32>(count);
@@ -1273,8 +1291,8 @@ int run_route(Ctx &c, const u32 *d_a, const u32 *d_b, u64 count, u64 add, u64 li
 int run_partition_by_splitters(Ctx &c, u64 *d_keys, u32 *d_pos, u64 count, const u64 *d_splitters, u32 nsplit,
                                u64 *d_keys_out, u32 *d_pos_out, u64 *counts_out)
 {
+    if (nsplit >= kRouteMaxRanks) return -1;                    // before touching counts_out (65 entries at the caller)
     for (u32 r = 0; r <= nsplit; ++r) counts_out[r] = 0;
-    if (nsplit >= kRouteMaxRanks) return -1;
     if (count == 0) return 0;
     void *temp = c.alloc(RadixSort<u64, u32>::temp_bytes(count));
     if (!temp) return -2;

@@ -80,7 +80,7 @@ static int partitioned_scatter(Ctx &c, const Gen &gen, u32 *ia, u32 *va, u32 *ib
         u64 *base = (u64 *)t;               t += kMaxPasses * kRadixSize * sizeof(u64);
         u32 *tickets = (u32 *)t;            t += 256;
         void *status = (void *)t;
-        const u64 nt = ceil_div(N, (u64)kPartTile);
+        const u64 nt = ceil_div(N, (u64)part_tile());
         const u32 dmask = (1u << (bits - lo)) - 1;
         if (!hist_ready) {
             c.check(cudaMemsetAsync(hist, 0, kRadixSize * sizeof(u64), c.stream));
@@ -93,11 +93,13 @@ static int partitioned_scatter(Ctx &c, const Gen &gen, u32 *ia, u32 *va, u32 *ib
         LSC_LAUNCH(c, kc, 0.0, sort_scan_kernel, 1, kRadixSize, 0, hist, base);
         c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * (N < (1ull << 30) ? sizeof(u32) : sizeof(u64)), c.stream));
         const double ab = (double)N * ((Gen::kActive ? 2.0 : 8.0) + 8.0);
+        PartArgs pa; pa.n = N; pa.shift = lo; pa.dmask = dmask; pa.base = base; pa.cp = nullptr; pa.nseg = 1; pa.tpc = (u32)nt;
+        pa.boff = nullptr; pa.tstart = nullptr; pa.ticket = tickets; pa.err = err; pa.use_bulk = 0;
         if constexpr (Gen::kActive) {
             FuncSrc<Gen> src; src.f = gen;
-            launch_part_pass<u32, u32, FuncSrc<Gen>, false>(c, kc, ab, src, (const u32 *)nullptr, (const u32 *)nullptr, ib, vb, N, nt, lo, dmask, base, SegArgs(), status, tickets, err);
+            launch_part_pass<u32, u32, FuncSrc<Gen>, false>(c, kc, ab, src, (const u32 *)nullptr, (const u32 *)nullptr, ib, vb, pa, nt, status);
         } else {
-            launch_part_pass<u32, u32, ArraySrc, false>(c, kc, ab, ArraySrc(), ia, va, ib, vb, N, nt, lo, dmask, base, SegArgs(), status, tickets, err);
+            launch_part_pass<u32, u32, ArraySrc, false>(c, kc, ab, ArraySrc(), ia, va, ib, vb, pa, nt, status);
         }
         if (c.failed()) return -2;
     }

@@ -66,6 +66,67 @@ def repetitive_dna(base_len, copies, seed=3, rate_num=1049):
     return out
 
 
+def _sm64_torch(x):
+    """splitmix64 finaliser over an int64 tensor (wrap-around arithmetic; logical shifts emulated with masks)."""
+    def lsr(v, s):
+        return (v >> s) & ((1 << (64 - s)) - 1)
+
+    def c(v):                                     # 64-bit constant as a signed python int
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    z = x + c(0x9E3779B97F4A7C15)
+    z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+    return z ^ lsr(z, 31)
+
+
+def dna_codes_torch(seed, n, device="cuda", chunk=1 << 26, start=0):
+    """Same 2-bit codes as dna_codes(), on the device."""
+    import torch
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        i = torch.arange(start + lo, start + hi, dtype=torch.int64, device=device)
+        z = _sm64_torch((seed << 40) + (i >> 5))
+        sh = (i & 31) * 2
+        code = torch.where(sh == 0, z & 3, ((z >> 1) & ((1 << 63) - 1)) >> (sh - 1).clamp(min=0)) & 3
+        out[lo:hi] = code.to(torch.uint8)
+    return out
+
+
+def repetitive_dna_torch(base_len, copies, seed=3, rate_num=1049, device="cuda"):
+    """Same text as repetitive_dna(), generated on the device (config c3: 1.9 GB takes minutes in numpy)."""
+    import torch
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    base = dna_codes_torch(seed, base_len, device=device)
+    out = torch.empty(base_len * copies, dtype=torch.uint8, device=device)
+    j = torch.arange(base_len, dtype=torch.int64, device=device)
+    for c in range(copies):
+        code = base
+        if c > 0:
+            u = _sm64_torch(((3000 + c) << 40) + j)
+            hit = (u & 0xFFFFF) < rate_num
+            um = (u >> 20) & ((1 << 44) - 1)                       # logical u >> 20
+            sub = (base.long() + 1 + (um % 3)) & 3
+            code = torch.where(hit, sub.to(torch.uint8), base)
+        out[c * base_len:(c + 1) * base_len] = lut[code.long()]
+    return out
+
+
+def rand_bytes_torch(seed, n, device="cuda", chunk=1 << 26):
+    """Same bytes as rand_bytes(), on the device."""
+    import torch
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        i = torch.arange(lo, hi, dtype=torch.int64, device=device)
+        z = _sm64_torch((seed << 40) + (i >> 3))
+        sh = (i & 7) * 8
+        v = torch.where(sh == 0, z & 255, ((z >> 1) & ((1 << 63) - 1)) >> (sh - 1).clamp(min=0)) & 255
+        out[lo:hi] = v.to(torch.uint8)
+    return out
+
+
 def dna_torch(seed, n, device="cuda", chunk=1 << 27):
     """Same iid ACGT text as dna(), generated on the device with torch integer ops (int64 wrap-around
     arithmetic; logical shifts emulated with masks).  For texts too large to generate on the host in time."""

@@ -40,3 +40,19 @@ if hi:
     for i, r in enumerate(data):
         reg[i // 50] += int(r[si])
     print("by 50-instr region:", {k * 50: round(100 * v / tot, 1) for k, v in sorted(reg.items())})
+# per CUDA source line (needs -lineinfo and --import-source on)
+cu = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(cu)))
+hi = [i for i, r in enumerate(rows) if r and 'Source' in r and any('Sampling' in c for c in r)]
+for h in hi[:1]:
+    hdr = rows[h]
+    try:
+        si = hdr.index('Warp Stall Sampling (All Samples)'); sc = hdr.index('Source'); ie = hdr.index('Instructions Executed')
+    except ValueError:
+        break
+    data = [r for r in rows[h + 1:] if len(r) > max(si, sc, ie) and r[si].replace(',', '').isdigit()]
+    tot = sum(int(r[si].replace(',', '')) for r in data) or 1
+    print("--- by CUDA source line (samples %d)" % tot)
+    top = sorted(((int(r[si].replace(',', '')), r[0], r[sc].strip(), r[ie]) for r in data), reverse=True)[:top_n]
+    for s, ln, t, e in top:
+        print("%6d %5.1f%% L%-5s x%-10s %s" % (s, 100 * s / tot, ln, e, t[:110]))
