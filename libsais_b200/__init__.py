@@ -120,6 +120,11 @@ class Context:
         return {"total_launches": int(s.total_launches), "device_ms": float(s.device_ms),
                 "workspace_bytes": int(s.workspace_bytes), "kernels": per, "rounds": rounds}
 
+    def release_workspace(self):
+        """Give the context's device workspace back (it is re-grown by the next call)."""
+        self.lib.libsais_cuda_release_workspace.argtypes = [C.c_void_p]
+        return int(self.lib.libsais_cuda_release_workspace(self.handle))
+
     def last_error(self):
         return int(self.lib.libsais_cuda_last_error(self.handle))
 

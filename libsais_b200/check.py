@@ -62,3 +62,30 @@ def verify_lcp(dP, dSA, dL, n, chunk=1 << 27):
         if not bool(torch.equal(dL[lo:lo + chunk], dP[dSA[lo:lo + chunk].long()])):
             return "LCP differs in [%d, %d)" % (lo, lo + chunk)
     return "ok"
+
+
+def verify_sa_u32(dT, dSA32, n, chunk=1 << 26):
+    """verify_sa for an SA stored as the low 32 bits of every entry (positions may exceed 2^31)."""
+    import torch
+    dev = dT.device
+    M = 0xFFFFFFFF
+    seen = torch.zeros(n, dtype=torch.uint8, device=dev)
+    for lo in range(0, n, chunk):
+        seen[dSA32[lo:lo + chunk].long() & M] = 1
+    if not bool(seen.all()):
+        return "not a permutation"
+    del seen
+    ISA = torch.empty(n, dtype=torch.int32, device=dev)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        ISA[dSA32[lo:hi].long() & M] = torch.arange(lo, hi, dtype=torch.int64, device=dev).to(torch.int32)
+    for lo in range(1, n, chunk):
+        hi = min(n, lo + chunk)
+        a = dSA32[lo - 1:hi - 1].long() & M; b = dSA32[lo:hi].long() & M
+        ta, tb = dT[a], dT[b]
+        ra = torch.where(a + 1 < n, ISA[torch.clamp(a + 1, max=n - 1)].long() & M, torch.full_like(a[:1], -1))
+        rb = torch.where(b + 1 < n, ISA[torch.clamp(b + 1, max=n - 1)].long() & M, torch.full_like(a[:1], -1))
+        ok = (ta < tb) | ((ta == tb) & (ra < rb))
+        if not bool(ok.all()):
+            return "order violated near slot %d" % (lo + int((~ok).nonzero()[0]))
+    return "ok"

@@ -73,7 +73,10 @@ struct PartArgs {
     u32 nseg, tpc;
     const u32 *boff;        // segmented: [65537] offsets of the 16-bit buckets
     const u32 *tstart;      // segmented: [257] exclusive scan of the tiles per top-level bucket
-    u32 *ticket; u32 *err; int use_bulk;
+    const uint2 *tinfo;     // segmented: per ticket (first element, count) from seg_tiles_kernel; count 0 = unused ticket
+    u32 *ticket;            // null: the ticket is blockIdx.x (CTAs are dispatched in index order, so a tile's predecessors are
+                            // always resident or done -- the same assumption CUB's decoupled look-back scan makes); else atomic
+    u32 *err; int use_bulk;
 };
 
 template <typename KeyT, typename ValT, int THREADS, int IPT, int MINB, typename ST, typename Src, bool SEG>
@@ -89,26 +92,24 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shift = a.shift; const u32 dmask = a.dmask;
 
+    uint2 ti = make_uint2(0, 0);
+    if (SEG && a.ticket == nullptr) ti = a.tinfo[blockIdx.x];        // issued before the barrier: one round trip saved
     if (tid == 0) {
-        sm.tile = atomicAdd(a.ticket, 1u);
+        sm.tile = a.ticket != nullptr ? atomicAdd(a.ticket, 1u) : blockIdx.x;
         mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1);
         mbar_fence_init();
     }
     if (tid < kRadixSize) sm.cnt[tid] = 0;
     __syncthreads();
-    const u32 ticket = sm.tile;
+    const u32 ticket = a.ticket != nullptr ? sm.tile : blockIdx.x;
     const u32 segi = ticket % a.nseg, j = ticket / a.nseg;           // segment, tile inside the segment
 
     // ---- which elements: [lo, lo + count) of the input
     u64 lo; u32 count;
     if (SEG) {
-        const u32 t0 = a.tstart[segi], t1 = a.tstart[segi + 1];
-        if (j >= t1 - t0) return;                                     // grid = nseg * (most tiles of any bucket)
-        const u64 blo = a.boff[segi << 8], bhi = a.boff[(segi + 1) << 8];
-        const u64 cell = blo / TILE + j;
-        const u64 clo = cell * TILE, chi = clo + TILE;
-        lo = blo > clo ? blo : clo;
-        count = (u32)((bhi < chi ? bhi : chi) - lo);
+        if (a.ticket != nullptr) ti = a.tinfo[ticket];
+        if (ti.y == 0) return;                                        // grid = nseg * (most tiles of any bucket)
+        lo = ti.x; count = ti.y;
     } else {
         const u64 tile = (u64)segi * a.tpc + j;
         lo = tile * TILE;
@@ -288,6 +289,24 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     }
 }
 
+// Ticket table of the segmented pass: ticket t = tile t / 256 of top-level bucket t % 256 -> (first element, count).
+static __global__ void __launch_bounds__(256)
+seg_tiles_kernel(const u32 *__restrict__ boff, const u32 *__restrict__ tstart, u32 tile, u32 grid, uint2 *__restrict__ tinfo)
+{
+    const u32 t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= grid) return;
+    const u32 segi = t % kRadixSize, j = t / kRadixSize;
+    uint2 r = make_uint2(0, 0);
+    if (j < tstart[segi + 1] - tstart[segi]) {
+        const u64 blo = boff[segi << 8], bhi = boff[(segi + 1) << 8];
+        const u64 cell = blo / tile + j;
+        const u64 clo = cell * tile, chi = clo + tile;
+        const u64 lo = blo > clo ? blo : clo;
+        r = make_uint2((u32)lo, (u32)((bhi < chi ? bhi : chi) - lo));
+    }
+    tinfo[t] = r;
+}
+
 // Tile shapes of the partition pass; LIBSAIS_CUDA_PART_VARIANT selects one (profiles/part_pass_r2.md).
 struct PartVariant { int threads, ipt, minb; };
 static const PartVariant kPartVariants[] = { {384, 12, 2}, {384, 10, 3}, {512, 8, 2}, {256, 12, 4} };
@@ -297,8 +316,8 @@ static inline int part_variant()
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("LIBSAIS_CUDA_PART_VARIANT");
-        v = (e && *e) ? atoi(e) : 0;
-        if (v < 0 || v >= kNumPartVariants) v = 0;
+        v = (e && *e) ? atoi(e) : 1;                                    // 384 x 10, three CTAs per SM: fastest on B200 (profiles/part_pass_r2.md)
+        if (v < 0 || v >= kNumPartVariants) v = 1;
     }
     return v;
 }
@@ -361,7 +380,7 @@ __device__ __forceinline__ void hist16_add(u32 *sh, u64 hi, u64 lw, int i)
 
 template <int B>
 static __global__ void __launch_bounds__(kHist16Threads, 1)
-hist16_kernel(const u64 *__restrict__ words, u64 n, u32 *__restrict__ hist, u32 *__restrict__ H, u32 nchunks, u64 chunk_elems,
+hist16_kernel(const u64 *__restrict__ words, u64 n, u32 *__restrict__ hist, u32 *__restrict__ H, u32 nunits, u32 upc, u32 ut, u32 tpc, u32 tile,
               u64 *__restrict__ flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -369,14 +388,20 @@ hist16_kernel(const u64 *__restrict__ words, u64 n, u32 *__restrict__ hist, u32 
     __shared__ u32 s_red[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int PER = 64 / B;                                    // suffixes whose window starts in one word
-    for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    // unit u = tiles [k * ut, (k + 1) * ut) of chunk s = u / upc (k = u % upc); the chunk's histogram H[s] is zeroed by the caller
+    for (u32 unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const u32 chunk = unit / upc, k = unit % upc;
+        const u64 tl0 = (u64)chunk * tpc + (u64)k * ut;
+        u64 tl1 = tl0 + ut;
+        if (tl1 > ((u64)chunk + 1) * tpc) tl1 = ((u64)chunk + 1) * tpc;
+        const u64 e0 = tl0 * tile;
+        const u64 e1 = tl1 * tile < n ? tl1 * tile : n;
+        if (tl0 >= tl1 || e0 >= n) continue;                            // uniform over the CTA
         {
             uint4 *z = reinterpret_cast<uint4 *>(sh);
             for (int i = tid; i < kHist16Words / 4; i += kHist16Threads) z[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
-        const u64 e0 = (u64)chunk * chunk_elems;
-        const u64 e1 = e0 + chunk_elems < n ? e0 + chunk_elems : n;
         const u64 p_lo = n - e1, p_hi = n - 1 - e0;                // positions of the chunk, inclusive
         const u64 w_first = (p_lo * B) >> 6, w_last = (p_hi * B) >> 6;
         for (u64 w = w_first + tid; w <= w_last; w += kHist16Threads) {
@@ -409,7 +434,7 @@ hist16_kernel(const u64 *__restrict__ words, u64 n, u32 *__restrict__ hist, u32 
         if (tid < kRadixSize) {
             u32 sum = 0;
             for (int k = 0; k < 128; ++k) { const u32 v = sh[tid * 128 + ((k + tid) & 127)]; sum += (v & 0xFFFFu) + (v >> 16); }
-            H[(u64)chunk * kRadixSize + tid] = sum;
+            if (sum) atomicAdd(&H[(u64)chunk * kRadixSize + tid], sum);
         }
         __syncthreads();
         if (tid == 0) {
@@ -550,10 +575,14 @@ __device__ __forceinline__ u32 lower_bound_u32(const u32 *__restrict__ a, u32 lo
 // tile j of bucket_sort = the buckets that start in [j*C, (j+1)*C): tb[j] = first bucket with boff >= j*C
 // (one thread per tile does the binary search once, so the sort CTAs start with a single load)
 static __global__ void __launch_bounds__(256)
-bucket_tiles_kernel(const u32 *__restrict__ boff, u64 ntiles, u32 C, u32 *__restrict__ tb)
+bucket_tiles_kernel(const u32 *__restrict__ boff, u64 ntiles, u32 C, uint4 *__restrict__ tb)
 {
     const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (j <= ntiles) tb[j] = lower_bound_u32(boff, 0, 65536, j * (u64)C);
+    if (j >= ntiles) return;
+    const u32 B0 = lower_bound_u32(boff, 0, 65536, j * (u64)C);
+    const u32 B1 = lower_bound_u32(boff, B0, 65536, (j + 1) * (u64)C);
+    const u32 s = boff[B0];
+    tb[j] = make_uint4(s, boff[B1] - s, B0, B1 - B0);                 // first element, count, first bucket, buckets
 }
 
 // exclusive scan of the packed 16-bit bin counters (8192 bins, thread t owns words [8t, 8t + 8)); afterwards the
@@ -593,19 +622,18 @@ __device__ __forceinline__ void bucket_bin_range(const BucketSmem &sm, u32 bin, 
 }
 
 static __global__ void __launch_bounds__(kBucketThreads, 2)
-bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, const u32 *__restrict__ boff, const u32 *__restrict__ tb,
+bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, const uint4 *__restrict__ tb,
                    u64 n, u32 C, int key_shift, int R,             // R = K - 16: k-mer bits below the bucket prefix
                    u64 *__restrict__ kout, u32 *__restrict__ vout, u32 *err)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BucketSmem &sm = *reinterpret_cast<BucketSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 B0 = tb[blockIdx.x], B1 = tb[blockIdx.x + 1];
-    const u64 s = boff[B0];
-    const u32 cnt = (u32)((u64)boff[B1] - s);
+    const uint4 ti = tb[blockIdx.x];
+    const u64 s = ti.x;
+    const u32 cnt = ti.y, B0 = ti.z, nb = ti.w;
     if (cnt == 0) return;
     if (cnt > (u32)kBucketCap) { if (tid == 0) *err = 3; return; }  // a bucket larger than promised
-    const u32 nb = B1 - B0;
     const int span_bits = R + (nb > 1 ? 32 - __clz(nb - 1) : 0);     // (k-mer - kbase) < 2^span_bits
     const int sh = span_bits > kBucketBinBits ? span_bits - kBucketBinBits : 0;
     const u64 kbase = (u64)B0 << R;

@@ -670,7 +670,7 @@ size_t sa_workspace_bytes(u64 n, int sym_bytes)
                               + 1);              /* lazy mode: separate small round buffers */
     size_t st = 3 * ceil_div(n, 32) * sizeof(u32) + ceil_div(n, kRankTile) * (kRankWarps + 1) * 3 * sizeof(u32) + 1024;
     size_t msd = (size_t)(65536 + 65540 + 257 + 1024 * 256) * 4 + 256 * 8 + (ceil_div(n, 3072) + 2048) * kRadixSize * 8
-               + (ceil_div(n, 1536) + 2) * 4 + 10 * 256;    // round-0 MSD path: prefix histogram, offsets, chunk prefixes, tile status, tile table
+               + (ceil_div(n, 1536) + 2) * 16 + (ceil_div(n, 3072) + 2048) * 8 + 12 * 256;    // round-0 MSD path: prefix histogram, offsets, chunk prefixes, tile status, tile table
     return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + msd + 256 + 32 * 256 + 4096;
 }
 
@@ -791,7 +791,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     u32 *m_boff = nullptr, *m_tstart = nullptr, *m_H = nullptr; u64 *m_base = nullptr; u64 m_maxb = 0, m_maxnt = 0;
     const u32 ptile = part_tile();
     const u64 nt1 = ceil_div(n, (u64)ptile);
-    u64 want_seg = (u64)c.sm_count * 2;                                             // chunks of the first pass
+    u64 want_seg = 16;                                                              // chunks of the first pass (profiles/part_pass_r2.md)
     { const char *env = getenv("LIBSAIS_CUDA_PART_NSEG"); if (env && *env && atoi(env) > 0) want_seg = (u64)atoi(env); }
     if (want_seg > 1024) want_seg = 1024;
     u32 nseg1 = (u32)(nt1 < want_seg ? nt1 : want_seg);
@@ -808,19 +808,23 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             if (!h16 || !m_boff || !m_tstart || !m_base || !m_H) return -2;
             c.check(cudaMemsetAsync(h16, 0, 65536 * sizeof(u32), st));
             c.check(cudaMemsetAsync(c.d_scalars + S_MSD, 0, 4 * sizeof(u64), st));
-            const u32 grid = nseg1 < (u32)c.sm_count ? nseg1 : (u32)c.sm_count;
-            const u64 chunk_elems = (u64)tpc * ptile;
+            // histogram units: every chunk is cut into upc units of ut tiles so that ~2 units per SM exist
+            const u32 q = (u32)ceil_div((u64)c.sm_count * 2, (u64)nseg1);
+            const u32 ut = (u32)ceil_div((u64)tpc, (u64)q), upc = (u32)ceil_div((u64)tpc, (u64)ut);
+            const u32 nunits = nseg1 * upc;
+            const u32 grid = nunits < (u32)c.sm_count ? nunits : (u32)c.sm_count;
+            c.check(cudaMemsetAsync(m_H, 0, (size_t)nseg1 * kRadixSize * sizeof(u32), st));
             const size_t hsm = kHist16Words * sizeof(u32);
             const double hb = (double)ceil_div(n * (u64)b, 64) * 8;
             u64 *flag = c.d_scalars + S_MSD + 2;
             if (b == 8)      { c.check(cudaFuncSetAttribute(hist16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<8>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<8>, grid, kHist16Threads, hsm, words, n, h16, m_H, nunits, upc, ut, tpc, ptile, flag); }
             else if (b == 4) { c.check(cudaFuncSetAttribute(hist16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<4>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<4>, grid, kHist16Threads, hsm, words, n, h16, m_H, nunits, upc, ut, tpc, ptile, flag); }
             else if (b == 2) { c.check(cudaFuncSetAttribute(hist16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<2>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<2>, grid, kHist16Threads, hsm, words, n, h16, m_H, nunits, upc, ut, tpc, ptile, flag); }
             else             { c.check(cudaFuncSetAttribute(hist16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<1>, grid, kHist16Threads, hsm, words, n, h16, m_H, nseg1, chunk_elems, flag); }
+                               LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<1>, grid, kHist16Threads, hsm, words, n, h16, m_H, nunits, upc, ut, tpc, ptile, flag); }
             LSC_LAUNCH(c, KC_SORT_SCAN, 65536.0 * 8, scan16_kernel, 1, 1024, 0, h16, m_boff, m_base, m_tstart, m_H, nseg1, c.d_scalars + S_MSD, ptile);
             c.check(cudaMemcpyAsync(c.h_scalars + S_MSD, c.d_scalars + S_MSD, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
             if (!c.sync()) return -2;
@@ -836,22 +840,27 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         u32 Cw = (u32)kBucketCap - (u32)m_maxb;
         if (Cw > 6144) Cw = 6144;
         const u64 btiles = ceil_div(n, (u64)Cw);
-        u32 *tb = c.alloc_n<u32>(btiles + 2);
-        if (!status || !tb) return -2;
+        uint4 *tb = c.alloc_n<uint4>(btiles + 1);
+        uint2 *tinfo = c.alloc_n<uint2>(grid2 + 1);
+        if (!status || !tb || !tinfo) return -2;
         u32 *tickets = (u32 *)(c.d_scalars + S_TICKET);
         c.check(cudaMemsetAsync(tickets, 0, 8 * sizeof(u64), st));
+        static const bool atomic_tickets = [] { const char *e = getenv("LIBSAIS_CUDA_TICKETS"); return e && *e && atoi(e) != 0; }();
         KmerSrc src; src.words = words; src.nwords = nwords; src.text = bwt_mode ? (const u8 *)d_T : nullptr; src.n = n; src.b = b; src.K = K; src.key_shift = key_shift;
         PartArgs pa; pa.n = n; pa.dmask = 255u; pa.err = err; pa.use_bulk = 0;
-        pa.shift = key_shift + K - 8; pa.base = m_base; pa.cp = m_H; pa.nseg = nseg1; pa.tpc = tpc; pa.boff = nullptr; pa.tstart = nullptr; pa.ticket = tickets;
+        pa.shift = key_shift + K - 8; pa.base = m_base; pa.cp = m_H; pa.nseg = nseg1; pa.tpc = tpc; pa.boff = nullptr; pa.tstart = nullptr; pa.tinfo = nullptr;
+        pa.ticket = atomic_tickets ? tickets : nullptr;
         c.check(cudaMemsetAsync(status, 0, grid1 * kRadixSize * stw, st));
         launch_part_pass<u64, u32, KmerSrc, false>(c, KC_SORT_PASS_GEN, (double)n * (2.0 + 12.0), src, (const u64 *)nullptr, (const u32 *)nullptr, keyA, valA, pa, grid1, status);
-        pa.shift = key_shift + K - 16; pa.base = nullptr; pa.cp = nullptr; pa.nseg = kRadixSize; pa.tpc = 0; pa.boff = m_boff; pa.tstart = m_tstart; pa.ticket = tickets + 1;
+        pa.shift = key_shift + K - 16; pa.base = nullptr; pa.cp = nullptr; pa.nseg = kRadixSize; pa.tpc = 0; pa.boff = m_boff; pa.tstart = m_tstart; pa.tinfo = tinfo;
+        pa.ticket = atomic_tickets ? tickets + 1 : nullptr;
+        LSC_LAUNCH(c, KC_SORT_HIST, 0.0, seg_tiles_kernel, (u32)ceil_div(grid2, 256), 256, 0, m_boff, m_tstart, ptile, (u32)grid2, tinfo);
         c.check(cudaMemsetAsync(status, 0, grid2 * kRadixSize * stw, st));
         launch_part_pass<u64, u32, ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
-        LSC_LAUNCH(c, KC_SORT_HIST, 0.0, bucket_tiles_kernel, (u32)ceil_div(btiles + 1, 256), 256, 0, m_boff, btiles, Cw, tb);
+        LSC_LAUNCH(c, KC_SORT_HIST, 0.0, bucket_tiles_kernel, (u32)ceil_div(btiles, 256), 256, 0, m_boff, btiles, Cw, tb);
         c.check(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
         LSC_LAUNCH(c, KC_BUCKET_SORT, (double)n * 24.0, bucket_sort_kernel, (u32)btiles, kBucketThreads, sizeof(BucketSmem),
-                   keyB, valB, m_boff, tb, n, Cw, key_shift, K - 16, keyA, valA, err);
+                   keyB, valB, tb, n, Cw, key_shift, K - 16, keyA, valA, err);
         rs.passes = 2;
         where = c.failed() ? -1 : 0;
     } else if (fuse_keys) {

@@ -1,0 +1,149 @@
+"""GPU parity tests added in round 2: the round-0 MSD path (partition.cuh), PLCP on texts with very long
+matches (the level-seeded compare), the batch entry point (BASELINE config 4) and the libsais64 host API
+beyond INT32_MAX.  Everything goes through the C-ABI and is compared with the oracle / compiled reference."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import _libs
+from libsais_b200 import gen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cu():
+    import libsais_b200
+    assert libsais_b200.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return _libs.cuda()
+
+
+def _best_cpu():
+    return _libs.ref() or _libs.oracle()
+
+
+def test_msd_and_lsd_round0_paths_agree(cu):
+    """Round 0 either partitions by the top 16 key bits and finishes the buckets in shared memory (MSD) or runs
+    the stable LSD passes: both must produce the oracle's SA and BWT.  Sizes straddle the tile (4608 / 3840)
+    and chunk boundaries; alphabets cover every code width the MSD path accepts (1, 2, 4, 8 bits)."""
+    o = _best_cpu()
+    rng = np.random.default_rng(77)
+    texts = [gen.rand_bytes(3, n) for n in (64, 100, 4607, 4608, 4609, 3840 * 3 + 1, 70_001, 1 << 20)]
+    texts += [gen.dna(7, n) for n in (4609, 300_000)]
+    texts += [(rng.integers(0, 16, 200_000) + 97).astype(np.uint8), (rng.integers(0, 2, 100_000) + 48).astype(np.uint8)]
+    texts += [np.concatenate([gen.rand_bytes(8, 50_000), np.zeros(37, dtype=np.uint8)]),       # zero tail: end-of-text rule
+              np.concatenate([np.zeros(9, dtype=np.uint8), gen.rand_bytes(9, 50_000)]),
+              np.tile(gen.rand_bytes(9, 20_000), 5)]                                            # exact repeats: many ties per bucket
+    try:
+        for T in texts:
+            rs, SAr = o.sa(T)
+            rb, Ur = o.bwt(T)
+            for mode in ("2", "0"):
+                os.environ["LIBSAIS_CUDA_MSD"] = mode
+                rc, SA = cu.sa(T)
+                assert rc == 0 and (SA == SAr).all(), (len(T), mode)
+                rcb, U = cu.bwt(T)
+                assert rcb == rb and (U == Ur).all(), (len(T), mode)
+                _, U2, I = cu.bwt_aux(T, 64)
+                assert (U2 == Ur).all() and (I == o.bwt_aux(T, 64)[2]).all(), (len(T), mode)
+    finally:
+        os.environ.pop("LIBSAIS_CUDA_MSD", None)
+
+
+def test_plcp_lcp_on_long_matches(cu):
+    """PLCP / LCP where neighbouring suffixes share thousands to millions of symbols (a^n, (ab)^n, a long period,
+    two identical halves, mutated copies): the compare must stay bounded (level seeding) and bit-exact."""
+    o = _best_cpu()
+    n = 1 << 20
+    texts = {"zeros": np.zeros(n, dtype=np.uint8), "abab": np.resize(np.frombuffer(b"ab", dtype=np.uint8), n + 1),
+             "period_1000": np.resize(gen.dna(3, 1000), n), "two_copies": np.concatenate([gen.dna(4, n // 2), gen.dna(4, n // 2)]),
+             "mutated_copies": gen.repetitive_dna(n // 64, 64), "tiny": np.frombuffer(b"banana", dtype=np.uint8).copy(),
+             "n33": np.resize(np.frombuffer(b"abc", dtype=np.uint8), 33), "n32": np.zeros(32, dtype=np.uint8)}
+    for name, T in texts.items():
+        for bits in (32, 64):
+            SA = o.sa(T, bits)[1]
+            p1, p2 = cu.plcp(T, SA, bits), o.plcp(T, SA, bits)
+            assert p1[0] == p2[0] == 0 and (p1[1] == p2[1]).all(), (name, bits)
+            l1, l2 = cu.lcp(p2[1], SA, bits), o.lcp(p2[1], SA, bits)
+            assert l1[0] == l2[0] == 0 and (l1[1] == l2[1]).all(), (name, bits)
+        Ti = T.astype(np.int32) * 1000 + 7
+        p1, p2 = cu.plcp(Ti, SA), _libs.oracle().plcp(Ti, SA)
+        assert (p1[1] == p2[1]).all(), name
+
+
+def test_bwt_batch_entry_point(cu):
+    """libsais_cuda_bwt_batch (BASELINE config 4's mechanism): 10 blocks of different sizes and alphabets through
+    the pooled contexts (3 host threads on the GPU), every block compared with the oracle; then the same blocks
+    with every visible GPU in the device list."""
+    import libsais_b200
+    lib = libsais_b200.load_library()
+    o = _best_cpu()
+    blocks = [gen.dna(1000 + b, 200_000 + 4099 * b) for b in range(6)] + [gen.rand_bytes(2000 + b, 150_000 + 777 * b) for b in range(4)]
+    blocks.append(np.frombuffer(b"x", dtype=np.uint8).copy())          # n = 1 fast path inside a batch
+    k = len(blocks)
+    outs = [np.zeros(len(b), dtype=np.uint8) for b in blocks]
+    Tp = (C.c_void_p * k)(*[b.ctypes.data for b in blocks])
+    Up = (C.c_void_p * k)(*[u.ctypes.data for u in outs])
+    ns = (C.c_int32 * k)(*[len(b) for b in blocks])
+    pr = (C.c_int32 * k)()
+    ms = (C.c_float * k)()
+    lib.libsais_cuda_bwt_batch.restype = C.c_int32
+    ndev = libsais_b200.device_count()
+    for devs in ([0], list(range(ndev)), None):
+        for u in outs:
+            u[:] = 0
+        dv = None if devs is None else (C.c_int32 * len(devs))(*devs)
+        rc = lib.libsais_cuda_bwt_batch(Tp, Up, ns, pr, ms, C.c_int32(k), dv, C.c_int32(0 if devs is None else len(devs)), C.c_int32(3))
+        assert rc == 0
+        for i, b in enumerate(blocks):
+            want = o.bwt(b)
+            assert int(pr[i]) == want[0] and (outs[i] == want[1]).all(), (devs, i)
+    assert lib.libsais_cuda_bwt_batch(None, Up, ns, pr, ms, C.c_int32(k), None, C.c_int32(0), C.c_int32(0)) == -1
+    bad = (C.c_int32 * 1)(ndev + 5)
+    assert lib.libsais_cuda_bwt_batch(Tp, Up, ns, pr, ms, C.c_int32(k), bad, C.c_int32(1), C.c_int32(0)) == -1
+    lib.libsais_cuda_batch_release()
+
+
+def test_libsais64_host_api_above_int32_max(cu):
+    """libsais64 through the HOST API with n = 2^31 + 1024 > INT32_MAX (iid ACGT, seed 5): the reference takes its
+    native 64-bit path (src/libsais64.c:7085); compared element by element with libsais64_omp of the compiled
+    reference when it travelled to this box (a few minutes of CPU), else checked by the linear-time verifier."""
+    import torch
+    import libsais_b200
+    from libsais_b200 import check
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip("needs ~130 GB of HBM")
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:
+        avail = 0
+    if avail < 60e9:
+        pytest.skip("needs ~45 GB of host memory")
+    n = (1 << 31) + 1024
+    T = gen.dna_torch(5, n, device="cuda").cpu().numpy()
+    lib = libsais_b200.load_library()
+    lib.libsais64.restype = C.c_int64
+    SA = np.empty(n, dtype=np.int64)
+    freq = np.zeros(256, dtype=np.int64)
+    rc = lib.libsais64(T.ctypes.data_as(C.c_void_p), SA.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int64(0), freq.ctypes.data_as(C.c_void_p))
+    assert rc == 0 and int(freq.sum()) == n
+    lib.libsais_cuda_release_workspace(None)
+    r = _libs.ref()
+    if r is not None and avail > 90e9:
+        SAr = np.empty(n, dtype=np.int64)
+        f = r.lib.libsais64_omp
+        f.restype = C.c_int64
+        assert f(T.ctypes.data_as(C.c_void_p), SAr.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int64(0), None, C.c_int64(0)) == 0
+        assert np.array_equal(SA, SAr)
+    else:
+        dT = torch.from_numpy(T).cuda()
+        d32 = torch.empty(n, dtype=torch.int32, device="cuda")
+        ch = 1 << 27
+        for lo in range(0, n, ch):
+            part = torch.from_numpy(SA[lo:lo + ch]).cuda()
+            assert int(part.min()) >= 0 and int(part.max()) < n
+            d32[lo:lo + ch] = part.to(torch.int32)                     # positions >= 2^31 wrap; the checker masks them back
+        assert check.verify_sa_u32(dT, d32, n) == "ok"
