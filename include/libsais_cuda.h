@@ -87,6 +87,22 @@ int32_t libsais_cuda_bwt_batch(const uint8_t * const * T, uint8_t * const * U, c
 /* Free the pooled contexts of libsais_cuda_bwt_batch (device workspaces, streams). */
 void    libsais_cuda_batch_release(void);
 
+/* ---- suffix array of ONE text over several GPUs of a node (BASELINE config 5): distributed prefix doubling with a sample
+ * sort, 64-bit positions; exchanges are P2P stores over NVLink issued by the routing kernel itself.  This is what
+ * libsais64() [reference include/libsais64.h:61] runs when n exceeds the single-GPU limit (2^32 - 16); $LIBSAIS_CUDA_DIST=G
+ * forces it with G GPUs for any n.  T: host text; SA: host int64[n] or NULL (result stays distributed, for timing);
+ * freq: nullable int64[256]; devices == NULL: GPUs 0..ndevices-1.  Returns 0, -1 (arguments) or -2. */
+typedef struct libsais_cuda_dist_stats {
+    int32_t  n_gpus, rounds, key_symbols, key_bits;
+    uint64_t slice_max;             /* largest slice of the suffix array held by one GPU */
+    uint64_t active_after_round0;   /* unresolved suffixes after the k-mer sort, all GPUs */
+    uint64_t exchanged_bytes;       /* bytes written into peer memory (NVLink), all GPUs */
+    double   seconds_total;         /* wall time of the call */
+    double   seconds_device;        /* from "packed text resident on every GPU" to "all SA slices final" */
+} libsais_cuda_dist_stats;
+int64_t libsais_cuda_sa64_multi(const uint8_t * T, int64_t * SA, int64_t n, int64_t * freq, const int32_t * devices, int32_t ndevices,
+                                libsais_cuda_dist_stats * stats);
+
 /* ---- building blocks of the distributed prefix doubling (texts beyond one GPU's working set; orchestrated by
  * libsais_b200/dist.py: one process per GPU, torch.distributed / NCCL all-to-alls between these calls).
  * Device pointers; every call completes before it returns. */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsais_cuda.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["ctx.cu", "hostcopy.cu", "sa_core.cu", "post.cu", "gsa.cu", "api.cu"]
+SOURCES = ["ctx.cu", "hostcopy.cu", "sa_core.cu", "post.cu", "gsa.cu", "dist64.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("LSC_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <new>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -137,11 +138,34 @@ template <typename IDX> u32 *upload_indexes(Ctx &c, const IDX *h_src, u64 count)
 // ------------------------------------------------------------------------------------------
 // generic bodies, IDX = int32_t (libsais_*) or int64_t (libsais64_*)
 // ------------------------------------------------------------------------------------------
+// libsais64 beyond one GPU: all visible GPUs (or $LIBSAIS_CUDA_DIST of them) run the distributed prefix doubling of dist64.cu
+int multi_gpu_count(u64 n)
+{
+    int want = 0;
+    const char *env = getenv("LIBSAIS_CUDA_DIST");
+    if (env && *env) want = atoi(env);
+    if (want <= 0 && n <= kMaxN) return 0;
+    int have = libsais_cuda_device_count();
+    if (have <= 0) return -1;
+    if (want <= 0) want = have;
+    return want;
+}
+
 template <typename IDX>
 IDX sa_body(Ctx *c, const uint8_t *T, IDX *SA, IDX n, IDX fs, IDX *freq)
 {
     if (T == nullptr || SA == nullptr || n < 0 || fs < 0) return -1;
     if (n < 2) { host_freq(T, n, freq); if (n == 1) SA[0] = 0; return 0; }
+    if (sizeof(IDX) == 8) {
+        const int G = multi_gpu_count((u64)n);
+        if (G < 0) return -2;
+        if (G > 0) {
+            int have = libsais_cuda_device_count();
+            std::vector<int> devs;
+            for (int i = 0; i < G; ++i) devs.push_back(i % have);          // more ranks than GPUs (testing): ranks share devices
+            return (IDX)sa64_multi(T, (i64 *)SA, (u64)n, (i64 *)freq, devs.data(), G, nullptr);
+        }
+    }
     if (!c || !c->ok || (u64)n > kMaxN) return -2;
     Call call(*c);
     if (!c->reserve((size_t)n + kPad + sa_workspace_bytes((u64)n, 1) + 4096)) return -2;
@@ -672,6 +696,25 @@ int32_t libsais_cuda_bwt_batch(const uint8_t *const *T, uint8_t *const *U, const
         for (int l = 0; l < lanes; ++l) th.emplace_back(worker, d, l);
     for (auto &t : th) t.join();
     return failed.load() ? -2 : 0;
+}
+
+int64_t libsais_cuda_sa64_multi(const uint8_t *T, int64_t *SA, int64_t n, int64_t *freq, const int32_t *devices, int32_t ndevices,
+                                libsais_cuda_dist_stats *stats)
+{
+    if (T == nullptr || n < 0 || ndevices < 1 || ndevices > 63) return -1;
+    if (n < 2) { if (freq) host_freq(T, n, freq); if (n == 1 && SA) SA[0] = 0; return 0; }
+    const int have = libsais_cuda_device_count();
+    if (have <= 0) return -2;
+    std::vector<int> devs;
+    for (int i = 0; i < ndevices; ++i) {
+        const int d = devices ? devices[i] : i % have;
+        if (d < 0 || d >= have) return -1;
+        devs.push_back(d);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = sa64_multi(T, (i64 *)SA, (u64)n, (i64 *)freq, devs.data(), ndevices, stats);
+    if (stats) stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 // Free the pooled contexts of the batch entry point (device workspaces, streams).

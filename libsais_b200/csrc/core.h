@@ -82,6 +82,12 @@ int run_partition_by_splitters(Ctx &c, u64 *d_keys, u32 *d_pos, u64 count, const
 size_t scatter_workspace_bytes(u64 count);
 void run_scatter_u32(Ctx &c, u32 *dst, u64 dst_len, const u32 *idx, const u32 *val, u64 count, u32 idx_offset);
 
+// exclusive max / sum / sum scans of the rank stage's tile aggregates tagg[3][ntiles]; totals of the sums -> out_counts[0..1]
+void run_rank_scan(Ctx &c, u32 *tagg, u64 ntiles, u64 *out_counts);
+
+// distributed prefix doubling over several GPUs of one node, 64-bit positions (dist64.cu)
+int sa64_multi(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int ndev, void *stats /* libsais_cuda_dist_stats, nullable */);
+
 // conversions used by the 64-bit API
 void run_widen(Ctx &c, const u32 *src, i64 *dst, u64 n);
 void run_narrow(Ctx &c, const i64 *src, u32 *dst, u64 n);

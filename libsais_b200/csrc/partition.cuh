@@ -77,6 +77,8 @@ struct PartArgs {
     u32 *ticket;            // null: the ticket is blockIdx.x (CTAs are dispatched in index order, so a tile's predecessors are
                             // always resident or done -- the same assumption CUB's decoupled look-back scan makes); else atomic
     u32 *err; int use_bulk;
+    void *const *kptr;      // non-null: per-digit output bases (device array of 256 pointers each), possibly in PEER memory:
+    void *const *vptr;      //   element i of digit d goes to kptr[d][i] / vptr[d][i] -- the fused route + exchange of dist64.cu
 };
 
 template <typename KeyT, typename ValT, int THREADS, int IPT, int MINB, typename ST, typename Src, bool SEG>
@@ -125,7 +127,7 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     u64 gbase = 0;
     if (tid < kRadixSize) {
         if (SEG) gbase = (u64)a.boff[(segi << 8) + tid];
-        else { gbase = a.base[tid]; if (a.cp != nullptr) gbase += (u64)a.cp[(u64)segi * kRadixSize + tid]; }
+        else if (a.kptr == nullptr) { gbase = a.base[tid]; if (a.cp != nullptr) gbase += (u64)a.cp[(u64)segi * kRadixSize + tid]; }
     }
     if constexpr (Src::kMode == SRC_KMER) {
         // positions of the tile: p_hi down to p_lo; words [w_lo, w_lo + nw) cover bits [p_lo*b, p_hi*b + 64 + 63]
@@ -188,7 +190,7 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
 #pragma unroll
             for (int i = 0; i < IPT; ++i) {
                 const u32 li = wbase + i * 32;
-                if (full || li < count) cp_async4(&sm.vals_in[li], vin + lo + li);
+                if (full || li < count) cp_async_val(&sm.vals_in[li], vin + lo + li);
             }
         }
     }
@@ -282,9 +284,15 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
         const u32 idx = i * THREADS + tid;
         if (full || idx < count) {
             const KeyT k = sm.keys[idx];
-            const u64 g = sm.goff[digit_of(k, shift, dmask)] + idx;
-            kout[g] = k;
-            vout[g] = sm.vals[idx];
+            const u32 d = digit_of(k, shift, dmask);
+            const u64 g = sm.goff[d] + idx;
+            if (a.kptr != nullptr) {
+                reinterpret_cast<KeyT *>(a.kptr[d])[g] = k;
+                reinterpret_cast<ValT *>(a.vptr[d])[g] = sm.vals[idx];
+            } else {
+                kout[g] = k;
+                vout[g] = sm.vals[idx];
+            }
         }
     }
 }

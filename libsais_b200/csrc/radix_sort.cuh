@@ -159,6 +159,15 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
     u32 d = (u32)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+template <typename T> __device__ __forceinline__ void cp_async_val(T *smem_dst, const T *gmem_src)
+{
+    if (sizeof(T) == 8) cp_async8(smem_dst, gmem_src); else cp_async4(smem_dst, gmem_src);
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one elected thread moves a
@@ -311,7 +320,7 @@ __device__ __forceinline__ void sort_pass_tile(PassSmem<KeyT, ValT, THREADS, IPT
 #pragma unroll
             for (int i = 0; i < IPT; ++i) {
                 u32 li = wbase + i * 32;
-                if (FULL || li < count) cp_async4(&sm.vals_in[VALS == 2 ? li : 0], vin + li);
+                if (FULL || li < count) cp_async_val(&sm.vals_in[VALS == 2 ? li : 0], vin + li);
             }
         }
     }
@@ -465,7 +474,7 @@ template <typename KeyT, typename ValT>
 struct RadixSort {
     static const int HIST_THREADS = 512;
 
-    static int tile_elems() { const PassVariant &pv = kPassVariants[pass_variant()]; return pv.threads * pv.ipt; }
+    static int tile_elems() { if (sizeof(ValT) == 8) return 256 * 16; const PassVariant &pv = kPassVariants[pass_variant()]; return pv.threads * pv.ipt; }
     static u64 tiles(u64 n) { return ceil_div(n, (u64)tile_elems()); }
 
     static size_t temp_bytes(u64 n)
@@ -506,6 +515,10 @@ struct RadixSort {
     static void pass(Ctx &c, const Gen &gen, const KeyT *kin, const ValT *vin, KeyT *kout, ValT *vout, u64 n,
                      int shift, u32 dmask, const u64 *base, u64 *status, u32 *ticket, u32 *err)
     {
+        if (sizeof(ValT) == 8) {            // 64-bit values (distributed path): the 4096-pair tile keeps two CTAs per SM
+            launch_pass<256, 16, 2, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err);
+            return;
+        }
         switch (pass_variant()) {
         case 1:  launch_pass<512, 8, 1, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err); break;
         case 2:  launch_pass<256, 16, 2, Gen>(c, gen, kin, vin, kout, vout, n, shift, dmask, base, status, ticket, err); break;

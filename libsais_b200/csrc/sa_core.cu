@@ -427,6 +427,11 @@ rank_scan_kernel(u32 *__restrict__ tagg, u64 ntiles, u64 *__restrict__ out_count
     }
 }
 
+void run_rank_scan(Ctx &c, u32 *tagg, u64 ntiles, u64 *out_counts)
+{
+    LSC_LAUNCH(c, KC_RANK_SCAN, (double)ntiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, tagg, ntiles, out_counts);
+}
+
 static const int kApplyTiles = 4;
 template <bool ROUND0>
 __global__ void __launch_bounds__(kRankThreads)
@@ -847,7 +852,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         c.check(cudaMemsetAsync(tickets, 0, 8 * sizeof(u64), st));
         static const bool atomic_tickets = [] { const char *e = getenv("LIBSAIS_CUDA_TICKETS"); return e && *e && atoi(e) != 0; }();
         KmerSrc src; src.words = words; src.nwords = nwords; src.text = bwt_mode ? (const u8 *)d_T : nullptr; src.n = n; src.b = b; src.K = K; src.key_shift = key_shift;
-        PartArgs pa; pa.n = n; pa.dmask = 255u; pa.err = err; pa.use_bulk = 0;
+        PartArgs pa; pa.n = n; pa.dmask = 255u; pa.err = err; pa.use_bulk = 0; pa.kptr = nullptr; pa.vptr = nullptr;
         pa.shift = key_shift + K - 8; pa.base = m_base; pa.cp = m_H; pa.nseg = nseg1; pa.tpc = tpc; pa.boff = nullptr; pa.tstart = nullptr; pa.tinfo = nullptr;
         pa.ticket = atomic_tickets ? tickets : nullptr;
         c.check(cudaMemsetAsync(status, 0, grid1 * kRadixSize * stw, st));

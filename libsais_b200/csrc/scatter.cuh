@@ -94,7 +94,7 @@ static int partitioned_scatter(Ctx &c, const Gen &gen, u32 *ia, u32 *va, u32 *ib
         c.check(cudaMemsetAsync(status, 0, nt * kRadixSize * (N < (1ull << 30) ? sizeof(u32) : sizeof(u64)), c.stream));
         const double ab = (double)N * ((Gen::kActive ? 2.0 : 8.0) + 8.0);
         PartArgs pa; pa.n = N; pa.shift = lo; pa.dmask = dmask; pa.base = base; pa.cp = nullptr; pa.nseg = 1; pa.tpc = (u32)nt;
-        pa.boff = nullptr; pa.tstart = nullptr; pa.tinfo = nullptr; pa.ticket = tickets; pa.err = err; pa.use_bulk = 0;
+        pa.boff = nullptr; pa.tstart = nullptr; pa.tinfo = nullptr; pa.ticket = tickets; pa.err = err; pa.use_bulk = 0; pa.kptr = nullptr; pa.vptr = nullptr;
         if constexpr (Gen::kActive) {
             FuncSrc<Gen> src; src.f = gen;
             launch_part_pass<u32, u32, FuncSrc<Gen>, false>(c, kc, ab, src, (const u32 *)nullptr, (const u32 *)nullptr, ib, vb, pa, nt, status);
