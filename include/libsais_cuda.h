@@ -99,6 +99,10 @@ typedef struct libsais_cuda_dist_stats {
     uint64_t exchanged_bytes;       /* bytes written into peer memory (NVLink), all GPUs */
     double   seconds_total;         /* wall time of the call */
     double   seconds_device;        /* from "packed text resident on every GPU" to "all SA slices final" */
+    int32_t  verify;                /* in: non-zero runs the distributed checker (ISA[SA[i]] == i and the neighbour-order rule for
+                                       every slot) on the device-resident result; out: 1 = proven correct, -1 = violations found */
+    int32_t  reserved;
+    uint64_t verify_violations;
 } libsais_cuda_dist_stats;
 int64_t libsais_cuda_sa64_multi(const uint8_t * T, int64_t * SA, int64_t n, int64_t * freq, const int32_t * devices, int32_t ndevices,
                                 libsais_cuda_dist_stats * stats);

@@ -306,6 +306,7 @@ struct DistGroup {
     u8 lut[256];
     std::vector<u64> splitters;
     libsais_cuda_dist_stats stats;
+    bool want_verify = false;
     std::mutex stats_mutex;
 };
 
@@ -374,6 +375,8 @@ struct DistRank {
     bool rank_stage(const u64 *keys, const u64 *pos, const u64 *slot_in, u64 N, u64 mask, u64 base, u64 *rank_out, u64 *sa_local,
                     u64 *a_pos, u64 *a_slot, u32 *a_grp, u64 *n_act, u64 *n_grp);
     bool update_isa(const u64 *pos, const u64 *rank, u64 count);
+    bool fetch_isa(const u64 *pos, u64 count, u64 add, u64 *out, bool ok_in);
+    bool verify(const u64 *sa_slice, u64 M, u64 base);
 };
 
 bool DistRank::rank_stage(const u64 *keys, const u64 *pos, const u64 *slot_in, u64 N, u64 mask, u64 base, u64 *rank_out, u64 *sa_local,
@@ -424,6 +427,139 @@ bool DistRank::update_isa(const u64 *pos, const u64 *rank, u64 count)
                           rkeys.as<u64>(), rvals.as<u64>(), total, lo, m, isa.as<u64>());
     ok = c->sync() && !c->failed();
     return sync_all_at(ok, __LINE__);                              // buffers are freed on return: nobody may still be writing
+}
+
+// out[j] = ISA[pos[j] + add] + 1 (0 when pos[j] + add >= n) for my `count` positions.  Collective: every rank calls it.
+// Requests go to the owners with the fused route (keys into the peers' request buffers, the element ids stay local in
+// destination order); every owner answers with one contiguous peer copy per requester.
+bool DistRank::fetch_isa(const u64 *pos, u64 count, u64 add, u64 *out, bool ok_in)
+{
+    const int G = g.G;
+    bool ok = ok_in;
+    DevBuf rk, idloc, idsrc, reqb, ansb, myans;
+    ok = ok && rk.alloc((count + 1) * 8) && idsrc.alloc((count + 1) * 8) && idloc.alloc((count + 1) * 8);
+    c->check(cudaMemsetAsync(cntd.p, 0, (kD64MaxRanks + 1) * 8, c->stream));
+    if (ok && count) LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)count * 24, d64_owner_keys_kernel, grid_stride(count), 256, 0,
+                                pos, count, add, g.n, g.B, (u32)G, rk.as<u64>(), idsrc.as<u64>(), cntd.as<u64>());
+    ok = ok && publish_counts();
+    if (!sync_all_at(ok, __LINE__)) return false;
+    const u64 nreq_in = recv_total();
+    u64 nreq_out = 0;
+    for (int d = 0; d < G; ++d) nreq_out += g.cnt[(size_t)r * (G + 1) + d];
+    ok = reqb.alloc((nreq_in + 1) * 8) && ansb.alloc((nreq_out + 1) * 8);
+    g.pk[r] = reqb.p; g.pans[r] = ansb.p;
+    if (!sync_all_at(ok, __LINE__)) return false;
+    {
+        void *kd[kD64MaxRanks + 1], *vd[kD64MaxRanks + 1];
+        for (int d = 0; d < G; ++d) { kd[d] = (u64 *)g.pk[d] + recv_offset(r, d); vd[d] = idloc.as<u64>() + send_offset(d); }
+        DevBuf dump;
+        ok = dump.alloc((g.cnt[(size_t)r * (G + 1) + G] + 1) * 8);
+        kd[G] = dump.p; vd[G] = dump.p;
+        ok = ok && route(rk.as<u64>(), idsrc.as<u64>(), count, kd, vd);
+    }
+    if (!sync_all_at(ok, __LINE__)) return false;
+    ok = myans.alloc((nreq_in + 1) * 8);
+    if (ok && nreq_in) LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)nreq_in * 24, d64_gather_kernel, grid_for(nreq_in), 256, 0,
+                                  reqb.as<u64>(), nreq_in, lo, m, isa.as<u64>(), myans.as<u64>());
+    if (ok) {
+        for (int s = 0; s < G; ++s) {
+            const u64 cnt_s = g.cnt[(size_t)s * (G + 1) + r];
+            if (!cnt_s) continue;
+            u64 off_in_s = 0;                                     // my block inside s's destination-ordered send list
+            for (int d = 0; d < r; ++d) off_in_s += g.cnt[(size_t)s * (G + 1) + d];
+            c->check(cudaMemcpyPeerAsync((u64 *)g.pans[s] + off_in_s, g.devs[s], myans.as<u64>() + recv_offset(s, r), g.devs[r], cnt_s * 8, c->stream));
+        }
+        exchanged_bytes += nreq_in * 16;
+        ok = c->sync();
+    }
+    if (!sync_all_at(ok, __LINE__)) return false;
+    if (count) {
+        LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)count * 8, d64_fill_kernel, grid_for(count), 256, 0, out, count, (u64)0);
+        if (nreq_out) LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)nreq_out * 24, d64_place_answers_kernel, grid_for(nreq_out), 256, 0, idloc.as<u64>(), ansb.as<u64>(), nreq_out, out);
+    }
+    ok = c->sync() && !c->failed();
+    return sync_all_at(ok, __LINE__);                             // the request / answer buffers die here: nobody may still be using them
+}
+
+// Distributed result check (no CPU reference exists at 2^34 symbols): with the final ISA slices,
+//   (1) ISA[SA[i]] == i for every slot i          => SA is a permutation of [0, n) and ISA its inverse
+//   (2) (T[SA[i-1]], ISA[SA[i-1]+1]) < (T[SA[i]], ISA[SA[i]+1]) for every i > 0 (rank past the end = -1)
+//       => every neighbouring pair is in suffix order (Burkhardt-Kaerkkaeinen)
+// which together prove the suffix array.  Two fetch_isa rounds + one streaming kernel; slice boundaries through the host.
+static __global__ void __launch_bounds__(256)
+d64_verify_kernel(const u64 *__restrict__ sa, const u64 *__restrict__ r0, const u64 *__restrict__ r1, u64 M, u64 base,
+                  const u64 *__restrict__ words, int b, u64 prev_sym, u64 prev_r1, int has_prev, u64 *__restrict__ bad, u64 *__restrict__ edge)
+{
+    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= M) return;
+    const u64 p = sa[j];
+    const u64 sym = kmer64_at(words, p, b, b);
+    u64 nbad = 0;
+    if (r0[j] != base + j + 1) nbad = 1;
+    u64 ps, pr; bool have = true;
+    if (j > 0) { ps = kmer64_at(words, sa[j - 1], b, b); pr = r1[j - 1]; }
+    else if (has_prev) { ps = prev_sym; pr = prev_r1; }
+    else { have = false; ps = pr = 0; }
+    if (have && !(ps < sym || (ps == sym && pr < r1[j]))) nbad = 1;
+    if (nbad) atomicAdd((unsigned long long *)bad, 1ull);
+    if (j == M - 1) { edge[0] = sym; edge[1] = r1[j]; }
+}
+
+bool DistRank::verify(const u64 *sa_slice, u64 M, u64 base)
+{
+    // in chunks of 2^27 slots, so the request / answer buffers stay small next to the resident SA and ISA slices;
+    // every rank runs the same number of chunks (the collectives inside fetch_isa must match)
+    const u64 CH = (u64)1 << 27;
+    g.scal[(size_t)r * 8 + 2] = M;
+    if (!sync_all_at(true, __LINE__)) return false;
+    u64 maxM = 0, total_m = 0;
+    for (int q = 0; q < g.G; ++q) { maxM = std::max(maxM, g.scal[(size_t)q * 8 + 2]); total_m += g.scal[(size_t)q * 8 + 2]; }
+    const u64 nchunks = ceil_div(maxM, CH);
+    DevBuf r0, r1, res;
+    const u64 cap = std::min(CH, M) + 1;
+    bool ok = r0.alloc(cap * 8) && r1.alloc(cap * 8) && res.alloc(64);
+    if (ok) c->check(cudaMemsetAsync(res.p, 0, 64, c->stream));
+    // the (symbol, next rank) of the element before the current chunk: from my previous chunk, or the last element of the
+    // nearest non-empty slice below mine (known after that rank's last chunk: published through the host at the end)
+    int has_prev = 0; u64 ps = 0, pr = 0;
+    u64 first_sym = 0, first_r1 = 0;             // my very first element, compared with the previous slice at the end
+    u64 last_sym = 0, last_r1 = 0;
+    for (u64 ch = 0; ch < nchunks; ++ch) {
+        const u64 c0 = std::min(M, ch * CH), c1 = std::min(M, c0 + CH), cn = c1 - c0;
+        if (!fetch_isa(sa_slice + c0, cn, 0, r0.as<u64>(), ok)) return false;
+        if (!fetch_isa(sa_slice + c0, cn, 1, r1.as<u64>(), true)) return false;
+        if (cn) {
+            LSC_LAUNCH(*c, KC_CONVERT, (double)cn * 24, d64_verify_kernel, grid_for(cn), 256, 0, sa_slice + c0, r0.as<u64>(), r1.as<u64>(), cn, base + c0,
+                       words.as<u64>(), g.b, ps, pr, has_prev, res.as<u64>(), res.as<u64>() + 1);
+            u64 e[2], f[2];
+            c->check(cudaMemcpyAsync(e, res.as<u64>() + 1, 16, cudaMemcpyDeviceToHost, c->stream));
+            c->check(cudaMemcpyAsync(f, sa_slice + c0, 8, cudaMemcpyDeviceToHost, c->stream));
+            c->check(cudaMemcpyAsync(f + 1, r1.as<u64>(), 8, cudaMemcpyDeviceToHost, c->stream));
+            ok = c->sync() && !c->failed();
+            if (ok) {
+                ps = e[0]; pr = e[1]; has_prev = 1; last_sym = e[0]; last_r1 = e[1];
+                if (c0 == 0) { first_sym = (u64)g.lut[g.T[f[0]]]; first_r1 = f[1]; }
+            }
+        }
+    }
+    u64 nbad = 0;
+    c->check(cudaMemcpyAsync(&nbad, res.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    ok = ok && c->sync() && !c->failed();
+    g.scal[(size_t)r * 8 + 3] = last_sym; g.scal[(size_t)r * 8 + 4] = last_r1; g.scal[(size_t)r * 8 + 5] = nbad;
+    if (!sync_all_at(ok, __LINE__)) return false;
+    // slice boundary: my first element against the last element of the nearest non-empty slice below
+    u64 edge_bad = 0;
+    if (M) for (int q = r - 1; q >= 0; --q) if (g.scal[(size_t)q * 8 + 2]) {
+        const u64 qs = g.scal[(size_t)q * 8 + 3], qr = g.scal[(size_t)q * 8 + 4];
+        if (!(qs < first_sym || (qs == first_sym && qr < first_r1))) edge_bad = 1;
+        break;
+    }
+    g.scal[(size_t)r * 8 + 6] = edge_bad;
+    if (!sync_all_at(true, __LINE__)) return false;
+    u64 total_bad = 0;
+    for (int q = 0; q < g.G; ++q) total_bad += g.scal[(size_t)q * 8 + 5] + g.scal[(size_t)q * 8 + 6];
+    if (r == 0) { std::lock_guard<std::mutex> lk(g.stats_mutex); g.stats.verify = (total_bad == 0 && total_m == g.n) ? 1 : -1; g.stats.verify_violations = total_bad; }
+    return sync_all_at(true, __LINE__);
 }
 
 int DistRank::run()
@@ -620,52 +756,13 @@ int DistRank::run()
         if (tot == 0) break;
         if (round > 80 || rank_bits + bits_for(maxg ? maxg : 1) > 63) { sync_all_at(false, __LINE__); return -2; }
         const u64 N = nact;
-        // requests: rank of suffix p + h from the owner of p + h (ids stay here, in destination order)
-        DevBuf rk, idloc;
-        ok = rk.alloc((N + 1) * 8) && ids.alloc((N + 1) * 8) && idloc.alloc((N + 1) * 8) && k2.alloc((N + 1) * 8);
-        c->check(cudaMemsetAsync(cntd.p, 0, (kD64MaxRanks + 1) * 8, st));
-        if (ok && N) LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)N * 24, d64_owner_keys_kernel, grid_stride(N), 256, 0,
-                                aPos[cur].as<u64>(), N, h, n, g.B, (u32)G, rk.as<u64>(), ids.as<u64>(), cntd.as<u64>());
-        ok = ok && publish_counts();
-        if (!sync_all_at(ok, __LINE__)) return -2;
-        const u64 nreq_in = recv_total();
-        u64 nreq_out = 0;
-        for (int d = 0; d < G; ++d) nreq_out += g.cnt[(size_t)r * (G + 1) + d];
-        ok = req.alloc((nreq_in + 1) * 8) && ans.alloc((nreq_out + 1) * 8);
-        g.pk[r] = req.p; g.pans[r] = ans.p;
-        if (!sync_all_at(ok, __LINE__)) return -2;
-        {
-            void *kd[kD64MaxRanks + 1], *vd[kD64MaxRanks + 1];
-            for (int d = 0; d < G; ++d) { kd[d] = (u64 *)g.pk[d] + recv_offset(r, d); vd[d] = idloc.as<u64>() + send_offset(d); }
-            DevBuf dump;
-            ok = dump.alloc((g.cnt[(size_t)r * (G + 1) + G] + 1) * 8);
-            kd[G] = dump.p; vd[G] = dump.p;
-            ok = ok && route(rk.as<u64>(), ids.as<u64>(), N, kd, vd);
-        }
-        if (!sync_all_at(ok, __LINE__)) return -2;
-        // answer the requests I received; every requester's block goes back to its answer buffer in its send order
-        DevBuf myans;
-        ok = myans.alloc((nreq_in + 1) * 8);
-        if (ok && nreq_in) LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)nreq_in * 24, d64_gather_kernel, grid_for(nreq_in), 256, 0,
-                                      req.as<u64>(), nreq_in, lo, m, isa.as<u64>(), myans.as<u64>());
-        if (ok) {
-            for (int s = 0; s < G; ++s) {
-                const u64 cnt_s = g.cnt[(size_t)s * (G + 1) + r];
-                if (!cnt_s) continue;
-                u64 off_in_s = 0;                                     // my block inside s's destination-ordered send list
-                for (int d = 0; d < r; ++d) off_in_s += g.cnt[(size_t)s * (G + 1) + d];
-                c->check(cudaMemcpyPeerAsync((u64 *)g.pans[s] + off_in_s, g.devs[s], myans.as<u64>() + recv_offset(s, r), g.devs[r], cnt_s * 8, st));
-            }
-            exchanged_bytes += nreq_in * 16;
-            ok = c->sync();
-        }
-        if (!sync_all_at(ok, __LINE__)) return -2;
+        // k2[j] = rank of suffix p_j + h, plus 1 (0 past the end): request / answer exchange with the position owners
+        ok = k2.alloc((N + 1) * 8);
+        if (!fetch_isa(ok ? aPos[cur].as<u64>() : nullptr, N, h, k2.as<u64>(), ok)) return -2;
         // keys (group, rank of the suffix h further + 1), local sort, rank stage
         ok = bufK[0].alloc((N + 1) * 8) && bufK[1].alloc((N + 1) * 8) && bufV[0].alloc((N + 1) * 8) && bufV[1].alloc((N + 1) * 8) && rankbuf.alloc((N + 1) * 8);
         u64 nact2 = 0, ngrp2 = 0;
         if (ok && N) {
-            LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)N * 8, d64_fill_kernel, grid_for(N), 256, 0, k2.as<u64>(), N, (u64)0);
-            if (nreq_out) LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)nreq_out * 24, d64_place_answers_kernel, grid_for(nreq_out), 256, 0, idloc.as<u64>(), ans.as<u64>(), nreq_out, k2.as<u64>());
             LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)N * 20, d64_round_keys_kernel, grid_for(N), 256, 0, aGrp.as<u32>(), k2.as<u64>(), N, rank_bits, bufK[0].as<u64>());
             c->check(cudaMemcpyAsync(bufV[0].p, aPos[cur].p, N * 8, cudaMemcpyDeviceToDevice, st));
             c->reset_arena();
@@ -697,6 +794,7 @@ int DistRank::run()
         std::lock_guard<std::mutex> lk(g.stats_mutex);
         g.stats.seconds_device = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     }
+    if (g.want_verify && !verify(sp, M, base)) return -2;
     // ---- my slice of the suffix array -> the caller's array
     if (g.SA != nullptr && M) {
         c->check(cudaMemcpyAsync(g.SA + base, sp, M * 8, cudaMemcpyDeviceToHost, st));
@@ -721,6 +819,8 @@ int sa64_multi(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int n
     g.B = ceil_div(ceil_div(n, (u64)ndev), 512) * 512;
     g.cnt.assign((size_t)ndev * (ndev + 1), 0); g.pk.assign(ndev, nullptr); g.pv.assign(ndev, nullptr); g.pwords.assign(ndev, nullptr); g.pans.assign(ndev, nullptr);
     g.scal.assign((size_t)ndev * 8, 0); g.hist.assign((size_t)ndev * 256, 0); g.samples.assign((size_t)ndev * kD64Samples, ~0ull);
+    g.want_verify = stats != nullptr && stats->verify != 0;
+    { const char *e = getenv("LIBSAIS_CUDA_DIST_VERIFY"); if (e && *e && atoi(e) != 0) g.want_verify = true; }
     std::memset(&g.stats, 0, sizeof(g.stats));
     std::vector<int> rc(ndev, 0);
     std::vector<std::thread> th;

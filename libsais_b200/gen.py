@@ -152,3 +152,10 @@ def dna_torch(seed, n, device="cuda", chunk=1 << 27):
         code = torch.where((i & 31) == 0, z & 3, code & 3)
         out[lo:hi] = lut[code]
     return out
+
+
+def dna_torch_range(seed, lo, hi, device="cuda"):
+    """Symbols [lo, hi) of dna(seed, .) on the device."""
+    import torch
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    return lut[dna_codes_torch(seed, hi - lo, device=device, start=lo).long()]

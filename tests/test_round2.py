@@ -147,3 +147,43 @@ def test_libsais64_host_api_above_int32_max(cu):
             assert int(part.min()) >= 0 and int(part.max()) < n
             d32[lo:lo + ch] = part.to(torch.int32)                     # positions >= 2^31 wrap; the checker masks them back
         assert check.verify_sa_u32(dT, d32, n) == "ok"
+
+
+class _DistStats(C.Structure):
+    _fields_ = [("n_gpus", C.c_int32), ("rounds", C.c_int32), ("key_symbols", C.c_int32), ("key_bits", C.c_int32),
+                ("slice_max", C.c_uint64), ("active_after_round0", C.c_uint64), ("exchanged_bytes", C.c_uint64),
+                ("seconds_total", C.c_double), ("seconds_device", C.c_double), ("verify", C.c_int32), ("reserved", C.c_int32),
+                ("verify_violations", C.c_uint64)]
+
+
+def test_distributed_prefix_doubling_in_library(cu):
+    """dist64.cu (BASELINE config 5's mechanism, what libsais64 runs beyond the single-GPU limit): G ranks -- one host
+    thread each, sharing GPUs when the box has fewer -- must return the reference's suffix array, and the distributed
+    checker must accept it.  Texts: iid (one doubling round), mutated copies / periodic / a^n (every suffix stays
+    unresolved for many rounds), tiny.  Also through libsais64() itself with $LIBSAIS_CUDA_DIST."""
+    import libsais_b200
+    lib = libsais_b200.load_library()
+    lib.libsais_cuda_sa64_multi.restype = C.c_int64
+    o = _best_cpu()
+    texts = [gen.dna(5, 1 << 19), gen.rand_bytes(2, 200_003), gen.repetitive_dna(10_000, 40), np.zeros(20_000, dtype=np.uint8),
+             np.resize(np.frombuffer(b"abracadabra", dtype=np.uint8), 100_003), np.frombuffer(b"mississippi", dtype=np.uint8).copy()]
+    for T in texts:
+        want = o.sa(T, 64)[1]
+        for G in (1, 2, 3, 5):
+            SA = np.full(len(T), -1, dtype=np.int64)
+            freq = np.zeros(256, dtype=np.int64)
+            st = _DistStats(); st.verify = 1
+            rc = lib.libsais_cuda_sa64_multi(T.ctypes.data_as(C.c_void_p), SA.ctypes.data_as(C.c_void_p), C.c_int64(len(T)),
+                                             freq.ctypes.data_as(C.c_void_p), None, C.c_int32(G), C.byref(st))
+            assert rc == 0 and (SA == want).all(), (len(T), G)
+            assert st.verify == 1 and st.n_gpus == G
+            assert (freq == np.bincount(T, minlength=256)).all()
+    try:
+        os.environ["LIBSAIS_CUDA_DIST"] = "2"
+        T = texts[0]
+        rc, SA = cu.sa(T, 64)
+        assert rc == 0 and (SA == o.sa(T, 64)[1]).all()
+    finally:
+        os.environ.pop("LIBSAIS_CUDA_DIST", None)
+    assert lib.libsais_cuda_sa64_multi(None, None, C.c_int64(5), None, None, C.c_int32(2), None) == -1
+    assert lib.libsais_cuda_sa64_multi(texts[0].ctypes.data_as(C.c_void_p), None, C.c_int64(len(texts[0])), None, None, C.c_int32(0), None) == -1
