@@ -103,6 +103,8 @@ typedef struct libsais_cuda_dist_stats {
                                        every slot) on the device-resident result; out: 1 = proven correct, -1 = violations found */
     int32_t  reserved;
     uint64_t verify_violations;
+    double   phase_seconds[8];      /* wall time on rank 0 between barriers: [0] round-0 keys + splitters + fused route, [1] local sort,
+                                       [2] rank stage, [3] ISA scatter (route + store), [4] all later rounds */
 } libsais_cuda_dist_stats;
 int64_t libsais_cuda_sa64_multi(const uint8_t * T, int64_t * SA, int64_t n, int64_t * freq, const int32_t * devices, int32_t ndevices,
                                 libsais_cuda_dist_stats * stats);

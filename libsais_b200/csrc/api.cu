@@ -267,6 +267,17 @@ IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *f
         if (aux) { I[0] = n; return 0; }
         return n;
     }
+    if (sizeof(IDX) == 8) {
+        const int G = multi_gpu_count((u64)n);
+        if (G < 0) return -2;
+        if (G > 0) {
+            int have = libsais_cuda_device_count();
+            std::vector<int> devs;
+            for (int i = 0; i < G; ++i) devs.push_back(i % have);
+            const i64 rc = bwt64_multi(T, U, (i64 *)A, (u64)n, (i64 *)freq, aux ? (u64)r : 0, aux ? (i64 *)I : nullptr, devs.data(), G);
+            return rc < 0 ? (IDX)rc : (aux ? (IDX)0 : (IDX)rc);
+        }
+    }
     if (!c || !c->ok || (u64)n > kMaxN) return -2;
     Call call(*c);
     const u64 n_aux = aux ? ((u64)n - 1) / (u64)r + 1 : 0;

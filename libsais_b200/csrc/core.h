@@ -87,6 +87,7 @@ void run_rank_scan(Ctx &c, u32 *tagg, u64 ntiles, u64 *out_counts);
 
 // distributed prefix doubling over several GPUs of one node, 64-bit positions (dist64.cu)
 int sa64_multi(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int ndev, void *stats /* libsais_cuda_dist_stats, nullable */);
+i64 bwt64_multi(const u8 *T, u8 *U, i64 *A, u64 n, i64 *freq, u64 aux_r, i64 *aux_I, const int *devices, int ndev);
 
 // conversions used by the 64-bit API
 void run_widen(Ctx &c, const u32 *src, i64 *dst, u64 n);

@@ -91,14 +91,16 @@ d64_dest_splitters_kernel(u64 *__restrict__ keys, u64 count, const u64 *__restri
         const u64 key = keys[i];
         u32 d = 0;
         for (u32 j = 0; j < nsplit; ++j) d += sp[j] <= key ? 1u : 0u;
-        keys[i] = key | ((u64)d << 56);
+        // keys travel RELATIVE to the lower splitter of their destination: the receiver sorts log2(G) fewer bits
+        keys[i] = (key - (d ? sp[d - 1] : 0)) | ((u64)d << 56);
         atomicAdd(&sh[d], 1u);
     }
     __syncthreads();
     if (threadIdx.x <= nsplit && sh[threadIdx.x]) atomicAdd((unsigned long long *)&dest_counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
-// routing key of a position: (owner << 56) | (pos + add); positions at or beyond `limit` get owner = world (dropped)
+// routing key of a position: (owner << 56) | offset of pos + add inside the owner's block; positions at or beyond `limit` get
+// owner = world (dropped)
 static __global__ void __launch_bounds__(256)
 d64_owner_keys_kernel(const u64 *__restrict__ pos, u64 count, u64 add, u64 limit, u64 block, u32 world,
                       u64 *__restrict__ keys, u64 *__restrict__ ident, u64 *__restrict__ dest_counts)
@@ -110,7 +112,7 @@ d64_owner_keys_kernel(const u64 *__restrict__ pos, u64 count, u64 add, u64 limit
         const u64 v = pos[i] + add;
         u64 owner = v < limit ? v / block : (u64)world;
         if (v < limit && owner >= world) owner = world - 1;
-        keys[i] = (owner << 56) | v;
+        keys[i] = (owner << 56) | (owner < world ? v - owner * block : v);
         if (ident != nullptr) ident[i] = i;
         atomicAdd(&sh[owner], 1u);
     }
@@ -122,20 +124,20 @@ static const u64 kLow56 = (((u64)1) << 56) - 1;
 
 // ISA[pos - lo] = rank for the received (routing key, rank) pairs
 static __global__ void __launch_bounds__(256)
-d64_scatter_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ ranks, u64 count, u64 lo, u64 len, u64 *__restrict__ ISA)
+d64_scatter_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ ranks, u64 count, u64 len, u64 *__restrict__ ISA)
 {
     const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i >= count) return;
-    const u64 j = (keys[i] & kLow56) - lo;
+    const u64 j = keys[i] & kLow56;
     if (j < len) ISA[j] = ranks[i];
 }
 // answers to the received requests: ISA[q - lo] + 1
 static __global__ void __launch_bounds__(256)
-d64_gather_kernel(const u64 *__restrict__ req, u64 count, u64 lo, u64 len, const u64 *__restrict__ ISA, u64 *__restrict__ ans)
+d64_gather_kernel(const u64 *__restrict__ req, u64 count, u64 len, const u64 *__restrict__ ISA, u64 *__restrict__ ans)
 {
     const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i >= count) return;
-    const u64 j = (req[i] & kLow56) - lo;
+    const u64 j = req[i] & kLow56;
     ans[i] = j < len ? ISA[j] + 1 : 0;
 }
 // keys of a doubling round: (group << rank_bits) | k2, k2 = answer of the request that carried this element's id (0: none)
@@ -156,6 +158,30 @@ d64_round_keys_kernel(const u32 *__restrict__ grp, const u64 *__restrict__ k2, u
 {
     const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
     if (i < count) keys[i] = ((u64)grp[i] << rank_bits) | k2[i];
+}
+
+// BWT rows of a slice of the suffix array: rows[j] = T[SA[j] - 1] (from the packed text through the inverse code map);
+// the slot of suffix 0 is reported (primary index - 1)
+static __global__ void __launch_bounds__(256)
+d64_bwt_rows_kernel(const u64 *__restrict__ sa, u64 M, u64 base, const u64 *__restrict__ words, int b, const u8 *__restrict__ inv,
+                    u8 *__restrict__ rows, u64 *__restrict__ primary)
+{
+    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= M) return;
+    const u64 p = sa[j];
+    u8 v = 0;
+    if (p == 0) *primary = base + j + 1;
+    else v = inv[(u32)kmer64_at(words, p - 1, b, b)];
+    rows[j] = v;
+}
+// aux samples of the owned positions: I[p / r] = ISA[p] + 1 for p % r == 0
+static __global__ void __launch_bounds__(256)
+d64_aux_kernel(const u64 *__restrict__ ISA, u64 lo, u64 count, u64 r, u64 first_idx, u64 nidx, i64 *__restrict__ out)
+{
+    const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (t >= nidx) return;
+    const u64 p = (first_idx + t) * r;
+    if (p >= lo && p - lo < count) out[t] = (i64)ISA[p - lo] + 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -273,15 +299,54 @@ struct HostBarrier {
     }
 };
 
+// Device memory of one rank: ONE cudaMalloc per call (cudaMalloc / cudaFree take a process-wide lock and cost milliseconds for
+// multi-GB blocks: with eight rank threads allocating dozens of buffers each they serialised the whole run), carved up by a
+// first-fit free list on the host.  A request that does not fit falls back to cudaMalloc, so the size estimate is not critical.
+struct Slab {
+    char *base = nullptr; size_t cap = 0;
+    std::vector<std::pair<size_t, size_t>> holes;          // (offset, size), sorted by offset
+    bool init(size_t bytes) {
+        if (cudaMalloc(&base, bytes) != cudaSuccess) { cudaGetLastError(); base = nullptr; return false; }
+        cap = bytes; holes.assign(1, std::make_pair((size_t)0, bytes));
+        return true;
+    }
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        for (size_t i = 0; i < holes.size(); ++i) if (holes[i].second >= bytes) {
+            void *p = base + holes[i].first;
+            holes[i].first += bytes; holes[i].second -= bytes;
+            if (holes[i].second == 0) holes.erase(holes.begin() + i);
+            return p;
+        }
+        return nullptr;
+    }
+    bool owns(const void *p) const { return base && (const char *)p >= base && (const char *)p < base + cap; }
+    void release(void *p, size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        const size_t off = (size_t)((char *)p - base);
+        size_t i = 0;
+        while (i < holes.size() && holes[i].first < off) ++i;
+        holes.insert(holes.begin() + i, std::make_pair(off, bytes));
+        if (i + 1 < holes.size() && holes[i].first + holes[i].second == holes[i + 1].first) { holes[i].second += holes[i + 1].second; holes.erase(holes.begin() + i + 1); }
+        if (i > 0 && holes[i - 1].first + holes[i - 1].second == holes[i].first) { holes[i - 1].second += holes[i].second; holes.erase(holes.begin() + i); }
+    }
+    ~Slab() { if (base) cudaFree(base); }
+};
+static thread_local Slab *tl_slab = nullptr;               // the slab of the rank thread that is running
+
 struct DevBuf {
-    void *p = nullptr; size_t bytes = 0;
+    void *p = nullptr; size_t bytes = 0; Slab *from = nullptr;
     bool alloc(size_t b) {
         release();
         if (b == 0) b = 256;
+        if (tl_slab != nullptr) { p = tl_slab->alloc(b); if (p) { from = tl_slab; bytes = b; return true; } }
         if (cudaMalloc(&p, b) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
-        bytes = b; return true;
+        from = nullptr; bytes = b; return true;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() {
+        if (p) { if (from) from->release(p, bytes); else cudaFree(p); }
+        p = nullptr; bytes = 0; from = nullptr;
+    }
     ~DevBuf() { release(); }
     template <typename T> T *as() const { return (T *)p; }
 };
@@ -293,6 +358,9 @@ struct DistGroup {
     std::atomic<int> failed{0};
     u64 n = 0, B = 0;
     const u8 *T = nullptr; i64 *SA = nullptr;
+    u8 *rows = nullptr;              // BWT mode: host scratch of n bytes for the per-slot rows (the caller's A array)
+    i64 *aux_I = nullptr; u64 aux_r = 0;
+    std::atomic<unsigned long long> primary{0};
     // shared metadata, indexed by rank
     std::vector<u64> cnt;            // [G][G+1] send counts of the current exchange: cnt[src * (G+1) + dst]
     std::vector<void *> pk, pv;      // receive buffers of the current exchange (keys / values)
@@ -314,6 +382,7 @@ static const int kD64Samples = 4096;
 
 struct DistRank {
     DistGroup &g; const int r; Ctx *c = nullptr;
+    Slab slab;                                 // declared before the buffers: destroyed after them
     u64 lo = 0, hi = 0, m = 0;                 // owned positions
     DevBuf words, isa, sa, bufK[2], bufV[2], rankbuf, flags, tagg, aPos[2], aSlot[2], aGrp, k2, ids, ans, req, cntd, ptrs, misc;
     u64 exchanged_bytes = 0;
@@ -349,7 +418,7 @@ struct DistRank {
 
     // The fused route + exchange: partition (keys, vals) by the destination in the keys' top byte; destination d's run is
     // written straight into kdst[d] / vdst[d] (peer memory).  Returns false on failure.
-    bool route(const u64 *keys, const u64 *vals, u64 count, void **kdst, void **vdst) {
+    bool route(const u64 *keys, const u64 *vals, u64 count, void **kdst, void **vdst, bool vals_remote = true) {
         if (count == 0) return true;
         c->reset_arena();
         void **h = (void **)(c->h_scalars + S_SGRAM);                      // pinned staging of the two pointer tables (G + 1 entries each)
@@ -366,7 +435,7 @@ struct DistRank {
         pa.boff = nullptr; pa.tstart = nullptr; pa.tinfo = nullptr; pa.ticket = nullptr; pa.err = (u32 *)(c->d_scalars + S_ERR); pa.use_bulk = 0;
         pa.kptr = (void *const *)ptrs.p; pa.vptr = (void *const *)((void **)ptrs.p + kRadixSize);
         launch_part_pass<u64, u64, ArraySrc, false>(*c, KC_SCATTER, (double)count * 32.0, ArraySrc(), keys, vals, (u64 *)nullptr, (u64 *)nullptr, pa, nt, status);
-        exchanged_bytes += count * 16;
+        exchanged_bytes += (count - g.cnt[(size_t)r * (g.G + 1) + r] - g.cnt[(size_t)r * (g.G + 1) + g.G]) * (vals_remote ? 16 : 8);   // bytes that leave this GPU
         if (!c->sync()) return false;                                      // the pointer staging is reused by the next route
         return !c->failed();
     }
@@ -423,9 +492,25 @@ bool DistRank::update_isa(const u64 *pos, const u64 *rank, u64 count)
     kd[G] = misc.p; vd[G] = misc.p;                   // nothing is dropped here (every position is < n)
     ok = route(rk.as<u64>(), rank, count, kd, vd);
     if (!sync_all_at(ok, __LINE__)) return false;                  // all peers' stores into my buffers are complete
-    if (total) LSC_LAUNCH(*c, KC_SCATTER, (double)total * 24, d64_scatter_kernel, grid_for(total), 256, 0,
-                          rkeys.as<u64>(), rvals.as<u64>(), total, lo, m, isa.as<u64>());
-    ok = c->sync() && !c->failed();
+    rk.release();
+    const u64 *fk = rkeys.as<u64>(), *fv = rvals.as<u64>();
+    DevBuf ak, av;
+    if (total >= ((u64)1 << 22) && m > ((u64)1 << 23)) {
+        // a random scatter of 8-byte words over a multi-GB slice runs at ~20 G/s: group the pairs by the top 8 bits of the
+        // offset first (one stable digit pass), so the stores walk the slice window by window and merge in L2 (scatter.cuh)
+        const int hb = bits_for(m - 1);
+        bool fits = ak.alloc((total + 1) * 8) && av.alloc((total + 1) * 8);
+        c->reset_arena();
+        void *temp = fits ? c->alloc(RadixSort<u64, u64>::temp_bytes(total)) : nullptr;
+        if (fits && temp) {
+            const int w = RadixSort<u64, u64>::sort(*c, rkeys.as<u64>(), rvals.as<u64>(), ak.as<u64>(), av.as<u64>(), total, hb > 8 ? hb - 8 : 0, hb, temp,
+                                                    (u32 *)(c->d_scalars + S_ERR));
+            if (w == 1) { fk = ak.as<u64>(); fv = av.as<u64>(); }
+            else if (w < 0) ok = false;
+        } else c->last_error = cudaSuccess;                          // no room: plain scatter
+    }
+    if (total) LSC_LAUNCH(*c, KC_SCATTER, (double)total * 24, d64_scatter_kernel, grid_for(total), 256, 0, fk, fv, total, m, isa.as<u64>());
+    ok = ok && c->sync() && !c->failed();
     return sync_all_at(ok, __LINE__);                              // buffers are freed on return: nobody may still be writing
 }
 
@@ -455,12 +540,12 @@ bool DistRank::fetch_isa(const u64 *pos, u64 count, u64 add, u64 *out, bool ok_i
         DevBuf dump;
         ok = dump.alloc((g.cnt[(size_t)r * (G + 1) + G] + 1) * 8);
         kd[G] = dump.p; vd[G] = dump.p;
-        ok = ok && route(rk.as<u64>(), idsrc.as<u64>(), count, kd, vd);
+        ok = ok && route(rk.as<u64>(), idsrc.as<u64>(), count, kd, vd, false);
     }
     if (!sync_all_at(ok, __LINE__)) return false;
     ok = myans.alloc((nreq_in + 1) * 8);
     if (ok && nreq_in) LSC_LAUNCH(*c, KC_ROUND_KEYS, (double)nreq_in * 24, d64_gather_kernel, grid_for(nreq_in), 256, 0,
-                                  reqb.as<u64>(), nreq_in, lo, m, isa.as<u64>(), myans.as<u64>());
+                                  reqb.as<u64>(), nreq_in, m, isa.as<u64>(), myans.as<u64>());
     if (ok) {
         for (int s = 0; s < G; ++s) {
             const u64 cnt_s = g.cnt[(size_t)s * (G + 1) + r];
@@ -469,7 +554,7 @@ bool DistRank::fetch_isa(const u64 *pos, u64 count, u64 add, u64 *out, bool ok_i
             for (int d = 0; d < r; ++d) off_in_s += g.cnt[(size_t)s * (G + 1) + d];
             c->check(cudaMemcpyPeerAsync((u64 *)g.pans[s] + off_in_s, g.devs[s], myans.as<u64>() + recv_offset(s, r), g.devs[r], cnt_s * 8, c->stream));
         }
-        exchanged_bytes += nreq_in * 16;
+        exchanged_bytes += (nreq_in - g.cnt[(size_t)r * (G + 1) + r]) * 8;   // answers that leave this GPU
         ok = c->sync();
     }
     if (!sync_all_at(ok, __LINE__)) return false;
@@ -588,8 +673,19 @@ int DistRank::run()
     lo = std::min(n, (u64)r * g.B); hi = std::min(n, lo + g.B); m = hi - lo;
     u32 *err = (u32 *)(c->d_scalars + S_ERR);
     c->check(cudaMemsetAsync(c->d_scalars + S_ERR, 0, (S_MISC - S_ERR) * sizeof(u64), st));
-    ok = cntd.alloc((kD64MaxRanks + 1) * sizeof(u64)) && ptrs.alloc(2 * kRadixSize * sizeof(void *)) && misc.alloc(1 << 20);
-    ok = ok && c->reserve((size_t)(RadixSort<u64, u64>::temp_bytes(m + m / 2 + 4096) + (ceil_div(m + m / 2, 3072) + 4096) * kRadixSize * 8 + (64 << 20)));
+    ok = c->reserve((size_t)(RadixSort<u64, u64>::temp_bytes(m + m / 2 + 4096) + (ceil_div(m + m / 2, 3072) + 4096) * kRadixSize * 8 + (64 << 20)));
+    if (ok) {   // the rank's slab: what the run is expected to need, at most this rank's share of the free memory
+        size_t fr = 0, tot = 0;
+        int share = 0;
+        for (int q = 0; q < G; ++q) share += g.devs[q] == g.devs[r] ? 1 : 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = 0; }
+        const size_t want = (size_t)(m + m / 6) * 88 + (size_t)n + ((size_t)512 << 20);
+        size_t give = (size_t)((double)fr * 0.94 / share);
+        if (give > want) give = want;
+        if (give >= ((size_t)64 << 20) && slab.init(give)) tl_slab = &slab;      // else: plain cudaMalloc per buffer
+        ok = cntd.alloc((kD64MaxRanks + 1) * sizeof(u64)) && ptrs.alloc(2 * kRadixSize * sizeof(void *)) && misc.alloc(1 << 20);
+    }
+    struct SlabGuard { ~SlabGuard() { tl_slab = nullptr; } } slab_guard;
     if (!sync_all_at(ok, __LINE__)) return -2;
 
     // ---- own slice of the text -> histogram -> (all ranks) alphabet -> packed slice -> replicated packed text
@@ -650,6 +746,14 @@ int DistRank::run()
     if (!sync_all_at(ok, __LINE__)) return -2;
     myw.release();
     const auto t_start = std::chrono::steady_clock::now();           // the packed text is resident on every GPU
+    auto t_last = t_start;
+    auto mark = [&](int slot) {                                       // rank 0, right after a barrier: phase wall times
+        if (r != 0) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::lock_guard<std::mutex> lk(g.stats_mutex);
+        g.stats.phase_seconds[slot] += std::chrono::duration<double>(now - t_last).count();
+        t_last = now;
+    };
 
     // ---- round 0: keys of the owned positions, splitters from a sample, fused route to the key owners, local sort
     const u64 cap0 = m + 1;
@@ -701,6 +805,7 @@ int DistRank::run()
         ok = route(bufK[0].as<u64>(), bufV[0].as<u64>(), m, kd, vd);
     }
     if (!sync_all_at(ok, __LINE__)) return -2;
+    mark(0);
     // local sort of the received pairs on the key bits (the destination byte is above them)
     ok = bufK[0].alloc((M + 1) * 8) && bufV[0].alloc((M + 1) * 8);
     int where = 1;
@@ -709,13 +814,20 @@ int DistRank::run()
         void *temp = c->alloc(RadixSort<u64, u64>::temp_bytes(M));
         ok = temp != nullptr;
         if (ok) {
-            const int w = RadixSort<u64, u64>::sort(*c, bufK[1].as<u64>(), bufV[1].as<u64>(), bufK[0].as<u64>(), bufV[0].as<u64>(), M, 0, key_bits, temp, err);
+            // my keys are relative to my lower splitter: their width is that of my key range
+            const u64 range_lo = r ? g.splitters[r - 1] : 0, range_hi = r + 1 < G ? g.splitters[r] : ((u64)1 << key_bits);
+            const int my_bits = range_hi > range_lo ? bits_for(range_hi - range_lo) : 1;
+            const int w = RadixSort<u64, u64>::sort(*c, bufK[1].as<u64>(), bufV[1].as<u64>(), bufK[0].as<u64>(), bufV[0].as<u64>(), M, 0,
+                                                    my_bits < key_bits ? my_bits : key_bits, temp, err);
             ok = w >= 0;
             where = w == 0 ? 1 : 0;                                   // sort() returns 0 when the result is in its first buffer pair (= bufK[1])
         }
     }
+    ok = ok && c->sync();
+    if (!sync_all_at(ok, __LINE__)) return -2;
+    mark(1);
     u64 *sk = where ? bufK[1].as<u64>() : bufK[0].as<u64>();          // sorted keys
-    std::swap(sa.p, bufV[where].p); std::swap(sa.bytes, bufV[where].bytes);   // the SA slice owns the sorted positions from here on
+    std::swap(sa.p, bufV[where].p); std::swap(sa.bytes, bufV[where].bytes); std::swap(sa.from, bufV[where].from);   // the SA slice owns the sorted positions from here on
     u64 *sp = sa.as<u64>();                                           // sorted positions = my slice of the SA (singletons are final)
     const int other = where ? 0 : 1;
     // rank stage: heads, ranks (global slot of the group head), unresolved suffixes
@@ -729,15 +841,27 @@ int DistRank::run()
     // keep the actives in right-sized buffers, free the big ones
     ok = aPos[0].alloc((nact + 1) * 8) && aPos[1].alloc((nact + 1) * 8) && aSlot[1].alloc((nact + 1) * 8);
     if (ok && nact) c->check(cudaMemcpyAsync(aPos[0].p, a_pos0, nact * 8, cudaMemcpyDeviceToDevice, st));
-    ok = ok && c->sync();
+    {   // the slot / group arrays were sized for the worst case (every suffix unresolved): move them to right-sized buffers
+        DevBuf s2, g2;
+        ok = ok && s2.alloc((nact + 1) * 8) && g2.alloc((nact + 1) * 4);
+        if (ok && nact) {
+            c->check(cudaMemcpyAsync(s2.p, aSlot[0].p, nact * 8, cudaMemcpyDeviceToDevice, st));
+            c->check(cudaMemcpyAsync(g2.p, aGrp.p, nact * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        ok = ok && c->sync();
+        std::swap(aSlot[0].p, s2.p); std::swap(aSlot[0].bytes, s2.bytes); std::swap(aSlot[0].from, s2.from);
+        std::swap(aGrp.p, g2.p); std::swap(aGrp.bytes, g2.bytes); std::swap(aGrp.from, g2.from);
+    }
     bufK[other].release();
     bufV[other].release();
     if (where) bufK[1].release(); else bufK[0].release();            // the sorted keys are dead; sp (positions) stays: it is the SA slice
     // ISA: ranks of ALL suffixes to the position owners
     ok = ok && isa.alloc((m + 1) * 8);
     if (!sync_all_at(ok, __LINE__)) return -2;
+    mark(2);
     if (!update_isa(sp, rankbuf.as<u64>(), M)) return -2;
     rankbuf.release();
+    mark(3);
     {
         std::lock_guard<std::mutex> lk(g.stats_mutex);
         g.stats.rounds = 1; g.stats.slice_max = std::max<u64>(g.stats.slice_max, M); g.stats.active_after_round0 += nact;
@@ -790,11 +914,46 @@ int DistRank::run()
         if (r == 0) { std::lock_guard<std::mutex> lk(g.stats_mutex); g.stats.rounds = round + 1; }
     }
 
+    mark(4);
     if (r == 0) {
         std::lock_guard<std::mutex> lk(g.stats_mutex);
         g.stats.seconds_device = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     }
     if (g.want_verify && !verify(sp, M, base)) return -2;
+    // ---- BWT rows / aux samples (libsais64_bwt[_aux] beyond the single-GPU limit): local, the packed text is replicated
+    if (g.rows != nullptr) {
+        DevBuf drows, dinv, dprim;
+        ok = drows.alloc(M + 1) && dinv.alloc(256) && dprim.alloc(8);
+        if (ok) {
+            u8 *h_inv = (u8 *)(c->h_scalars + S_MISC);
+            for (int s2 = 0; s2 < 256; ++s2) h_inv[s2] = 0;
+            for (int s2 = 0; s2 < 256; ++s2) if (g.hist[s2]) h_inv[g.lut[s2]] = (u8)s2;
+            c->check(cudaMemcpyAsync(dinv.p, h_inv, 256, cudaMemcpyHostToDevice, st));
+            c->check(cudaMemsetAsync(dprim.p, 0, 8, st));
+            if (M) {
+                LSC_LAUNCH(*c, KC_BWT, (double)M * 10, d64_bwt_rows_kernel, grid_for(M), 256, 0, sp, M, base, words.as<u64>(), b, dinv.as<u8>(), drows.as<u8>(), dprim.as<u64>());
+                c->check(cudaMemcpyAsync(g.rows + base, drows.p, M, cudaMemcpyDeviceToHost, st));
+            }
+            u64 pr = 0;
+            c->check(cudaMemcpyAsync(&pr, dprim.p, 8, cudaMemcpyDeviceToHost, st));
+            ok = c->sync() && !c->failed();
+            if (ok && pr) g.primary.store(pr);
+        }
+        if (ok && g.aux_I != nullptr && g.aux_r && m) {
+            const u64 first_idx = ceil_div(lo, g.aux_r), last_idx = (hi - 1) / g.aux_r;
+            if (last_idx >= first_idx) {
+                const u64 nidx = last_idx - first_idx + 1;
+                DevBuf dI;
+                ok = dI.alloc(nidx * 8);
+                if (ok) {
+                    LSC_LAUNCH(*c, KC_BWT, (double)nidx * 16, d64_aux_kernel, grid_for(nidx), 256, 0, isa.as<u64>(), lo, m, g.aux_r, first_idx, nidx, dI.as<i64>());
+                    c->check(cudaMemcpyAsync(g.aux_I + first_idx, dI.p, nidx * 8, cudaMemcpyDeviceToHost, st));
+                    ok = c->sync() && !c->failed();
+                }
+            }
+        }
+        if (!sync_all_at(ok, __LINE__)) return -2;
+    }
     // ---- my slice of the suffix array -> the caller's array
     if (g.SA != nullptr && M) {
         c->check(cudaMemcpyAsync(g.SA + base, sp, M * 8, cudaMemcpyDeviceToHost, st));
@@ -809,13 +968,15 @@ int DistRank::run()
 }
 
 // Suffix array of a HOST text over the given GPUs (one host thread per GPU).  SA may be NULL (timing / memory tests).
-int sa64_multi(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int ndev, void *stats_out)
+static int sa64_multi_impl(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int ndev, void *stats_out,
+                           u8 *rows, i64 *aux_I, u64 aux_r, u64 *primary_out)
 {
     libsais_cuda_dist_stats *stats = (libsais_cuda_dist_stats *)stats_out;
     if (ndev < 1 || ndev > kD64MaxRanks - 1 || n < 2) return -1;
     DistGroup g;
     g.G = ndev; g.devs.assign(devices, devices + ndev);
     g.bar.n = ndev; g.n = n; g.T = T; g.SA = SA;
+    g.rows = rows; g.aux_I = aux_I; g.aux_r = aux_r;
     g.B = ceil_div(ceil_div(n, (u64)ndev), 512) * 512;
     g.cnt.assign((size_t)ndev * (ndev + 1), 0); g.pk.assign(ndev, nullptr); g.pv.assign(ndev, nullptr); g.pwords.assign(ndev, nullptr); g.pans.assign(ndev, nullptr);
     g.scal.assign((size_t)ndev * 8, 0); g.hist.assign((size_t)ndev * 256, 0); g.samples.assign((size_t)ndev * kD64Samples, ~0ull);
@@ -832,7 +993,32 @@ int sa64_multi(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int n
     for (int r = 0; r < ndev; ++r) if (rc[r] != 0) out = -2;
     if (out == 0 && freq != nullptr) for (int s = 0; s < 256; ++s) freq[s] = (i64)g.hist[s];
     if (stats) { *stats = g.stats; stats->n_gpus = ndev; stats->key_symbols = g.k; stats->key_bits = g.K; }
+    if (primary_out) *primary_out = g.primary.load();
     return out;
+}
+
+int sa64_multi(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int ndev, void *stats_out)
+{
+    return sa64_multi_impl(T, SA, n, freq, devices, ndev, stats_out, nullptr, nullptr, 0, nullptr);
+}
+
+// BWT (+ aux samples) of a host text over several GPUs: libsais64_bwt[_aux] beyond the single-GPU limit
+// (reference src/libsais64.c:7133, :7172).  A (the caller's temporary int64[n]) holds the n per-slot rows while the ranks work;
+// U may alias T (every rank has consumed its slice of T before anything is written).  Returns the primary index or < 0.
+i64 bwt64_multi(const u8 *T, u8 *U, i64 *A, u64 n, i64 *freq, u64 aux_r, i64 *aux_I, const int *devices, int ndev)
+{
+    u8 *rows = (u8 *)A;
+    const u8 last = T[n - 1];
+    u64 primary = 0;
+    const int rc = sa64_multi_impl(T, nullptr, n, freq, devices, ndev, nullptr, rows, aux_I, aux_r, &primary);
+    if (rc != 0) return rc;
+    if (primary < 1 || primary > n) return -2;
+    // U[0] = T[n-1]; slot i < p0 -> U[i+1]; slot i > p0 -> U[i]  (the row of the virtual sentinel is dropped; p0 = primary - 1)
+    const u64 p0 = primary - 1;
+    U[0] = last;
+    std::memmove(U + 1, rows, p0);
+    std::memmove(U + p0 + 1, rows + p0 + 1, n - 1 - p0);
+    return (i64)primary;
 }
 
 }  // namespace lsc

@@ -153,7 +153,7 @@ class _DistStats(C.Structure):
     _fields_ = [("n_gpus", C.c_int32), ("rounds", C.c_int32), ("key_symbols", C.c_int32), ("key_bits", C.c_int32),
                 ("slice_max", C.c_uint64), ("active_after_round0", C.c_uint64), ("exchanged_bytes", C.c_uint64),
                 ("seconds_total", C.c_double), ("seconds_device", C.c_double), ("verify", C.c_int32), ("reserved", C.c_int32),
-                ("verify_violations", C.c_uint64)]
+                ("verify_violations", C.c_uint64), ("phase_seconds", C.c_double * 8)]
 
 
 def test_distributed_prefix_doubling_in_library(cu):
@@ -187,3 +187,26 @@ def test_distributed_prefix_doubling_in_library(cu):
         os.environ.pop("LIBSAIS_CUDA_DIST", None)
     assert lib.libsais_cuda_sa64_multi(None, None, C.c_int64(5), None, None, C.c_int32(2), None) == -1
     assert lib.libsais_cuda_sa64_multi(texts[0].ctypes.data_as(C.c_void_p), None, C.c_int64(len(texts[0])), None, None, C.c_int32(0), None) == -1
+
+
+def test_distributed_bwt_through_libsais64_bwt(cu):
+    """libsais64_bwt / libsais64_bwt_aux on the multi-GPU path ($LIBSAIS_CUDA_DIST forces it at small n): BWT rows come from
+    the distributed SA slices and the replicated packed text, aux samples from the ISA slices; in place (U == T) too."""
+    o = _best_cpu()
+    texts = [gen.dna(6, 300_001), gen.rand_bytes(3, 100_000), gen.repetitive_dna(5_000, 30), np.zeros(5_000, dtype=np.uint8)]
+    try:
+        for G in ("1", "2", "3"):
+            os.environ["LIBSAIS_CUDA_DIST"] = G
+            for T in texts:
+                want = o.bwt(T, 64)
+                got = cu.bwt(T, 64, want_freq=True)
+                assert got[0] == want[0] and (got[1] == want[1]).all(), (G, len(T))
+                assert (got[2] == np.bincount(T, minlength=256)).all()
+                wa = o.bwt_aux(T, 256, 64)
+                ga = cu.bwt_aux(T, 256, 64)
+                assert ga[0] == 0 and (ga[1] == wa[1]).all() and (ga[2] == wa[2]).all(), (G, len(T))
+                buf = T.copy()
+                gi = cu.bwt(buf, 64, inplace=True)
+                assert gi[0] == want[0] and (gi[1] == want[1]).all()
+    finally:
+        os.environ.pop("LIBSAIS_CUDA_DIST", None)

@@ -47,7 +47,8 @@ def main():
                "wall_s_incl_upload_and_check": round(wall, 2), "mbs_device": round(n / 1e6 / max(st.seconds_device, 1e-9), 1),
                "rounds": st.rounds, "key_symbols": st.key_symbols, "slice_max": st.slice_max, "unresolved_after_round0": st.active_after_round0,
                "nvlink_bytes": st.exchanged_bytes, "nvlink_gbs_per_gpu_avg_over_run": round(st.exchanged_bytes / G / max(st.seconds_device, 1e-9) / 1e9, 1),
-               "proven_by_distributed_checker": st.verify == 1, "violations": st.verify_violations}
+               "proven_by_distributed_checker": st.verify == 1, "violations": st.verify_violations,
+               "phase_s": {k: round(st.phase_seconds[i], 3) for i, k in enumerate(("keys_route", "local_sort", "rank_stage", "isa_scatter", "later_rounds"))}}
         print(json.dumps(rec), flush=True)
 
 

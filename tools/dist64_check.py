@@ -18,7 +18,7 @@ class DistStats(C.Structure):
     _fields_ = [("n_gpus", C.c_int32), ("rounds", C.c_int32), ("key_symbols", C.c_int32), ("key_bits", C.c_int32),
                 ("slice_max", C.c_uint64), ("active_after_round0", C.c_uint64), ("exchanged_bytes", C.c_uint64),
                 ("seconds_total", C.c_double), ("seconds_device", C.c_double), ("verify", C.c_int32), ("reserved", C.c_int32),
-                ("verify_violations", C.c_uint64)]
+                ("verify_violations", C.c_uint64), ("phase_seconds", C.c_double * 8)]
 
 
 def run(lib, T, G, want_sa=True, verify=True):
