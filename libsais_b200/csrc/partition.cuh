@@ -297,6 +297,293 @@ part_pass_kernel(const KeyT *__restrict__ kin, const ValT *__restrict__ vin,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent, double-buffered variant of the partition pass (round-0 MSD levels; u64 keys, u32 values).
+// profiles/part_pass_r2.md: in the one-tile-per-CTA kernel ~40 % of all stall samples sit in the start-up chain of a tile
+// (ticket -> tile table -> TMA issue -> DRAM latency), with only 2-3 CTAs per SM to hide it.  Here a CTA walks tickets
+// blockIdx.x, + gridDim.x, ... and, while it ranks / scatters / writes out tile k, the loads of tile k+1 are already in
+// flight into the other stage: TMA bulk copies completing on per-stage mbarriers (array source), cp.async of the tile's
+// slice of the packed text and of the raw text (k-mer source).  The tile table entry is fetched two tiles ahead.
+// All CTAs are resident (grid <= occupancy), so the chained scan cannot deadlock.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, int IPT, int MODE>
+struct PipeSmem {
+    static const int TILE = THREADS * IPT;
+    static const int WMAX = TILE / 8 + 8;                       // k-mer source: words of one tile at <= 8 bits per symbol
+    static const int TMAX = TILE / 4 + 8;                       // raw text of one tile as 32-bit words
+    alignas(16) u64 kst[MODE == SRC_ARRAYS ? 2 : 1][TILE];      // TMA staging per stage; the current stage then holds the tile in digit order
+    alignas(16) u32 vst[MODE == SRC_ARRAYS ? 2 : 1][MODE == SRC_ARRAYS ? TILE : 4];
+    alignas(16) u32 vals[TILE];
+    alignas(16) u64 wst[MODE == SRC_KMER ? 2 : 1][MODE == SRC_KMER ? WMAX : 2];
+    alignas(16) u32 tst[MODE == SRC_KMER ? 2 : 1][MODE == SRC_KMER ? TMAX : 2];
+    u64  goff[kRadixSize];
+    u32  cnt[kRadixSize];
+    u32  tileoff[kRadixSize];
+    u32  scan_tmp[32];
+    alignas(8) u64 mbar[2][2];                                  // [stage][keys / values]
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int THREADS, int IPT, int MINB, typename ST, typename Src, bool SEG>
+__global__ void __launch_bounds__(THREADS, MINB)
+part_pipe_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout, u32 *__restrict__ vout,
+                 const PartArgs a, ST *status, const Src src, const u32 ntickets)
+{
+    typedef PipeSmem<THREADS, IPT, Src::kMode> Smem;
+    constexpr int TILE = THREADS * IPT;
+    static_assert(THREADS >= kRadixSize && THREADS % 32 == 0, "one thread per digit is assumed");
+    static_assert(Src::kMode == SRC_ARRAYS || Src::kMode == SRC_KMER, "array or k-mer source");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shift = a.shift; const u32 dmask = a.dmask;
+    const u32 stride = gridDim.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.mbar[s][0], 1); mbar_init(&sm.mbar[s][1], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // range of a ticket: (first element, count); count 0 = nothing to do
+    auto range_of = [&](u32 t, uint2 ti, u64 &lo, u32 &count) {
+        if (SEG) { lo = ti.x; count = ti.y; return; }
+        const u32 segi = t % a.nseg, j = t / a.nseg;
+        const u64 tile = (u64)segi * a.tpc + j;
+        lo = tile * TILE; count = 0;
+        if (j < a.tpc && lo < a.n) count = (u32)((a.n - lo) < (u64)TILE ? (a.n - lo) : (u64)TILE);
+    };
+    // issue the loads of a tile into stage s.  Array source: two TMA bulk copies (full, aligned tiles only; other tiles are
+    // loaded synchronously when they are processed).  K-mer source: cp.async of the words / text slices, one commit group.
+    auto issue = [&](int s, u64 lo, u32 count) {
+        if constexpr (Src::kMode == SRC_ARRAYS) {
+            const bool bulk = count == (u32)TILE && a.use_bulk && ((lo * 4) & 15) == 0;
+            if (bulk && tid == 0) {
+                fence_proxy_async();                                   // the stage was last touched through the generic proxy
+                mbar_expect_tx(&sm.mbar[s][0], (u32)(TILE * 8));
+                bulk_load(sm.kst[s], kin + lo, (u32)(TILE * 8), &sm.mbar[s][0]);
+                mbar_expect_tx(&sm.mbar[s][1], (u32)(TILE * 4));
+                bulk_load(sm.vst[s], vin + lo, (u32)(TILE * 4), &sm.mbar[s][1]);
+            }
+        } else {
+            if (count) {
+                const u64 p_hi = src.n - 1 - lo, p_lo = p_hi - (count - 1);
+                const u64 w_lo = (p_lo * (u64)src.b) >> 6;
+                u64 w_hi = ((p_hi * (u64)src.b) >> 6) + 1;
+                if (w_hi > src.nwords - 1) w_hi = src.nwords - 1;
+                const u32 nw = (u32)(w_hi - w_lo + 1);
+                for (u32 i = tid; i < nw && i < (u32)Smem::WMAX; i += THREADS) cp_async8(&sm.wst[s][i], src.words + w_lo + i);
+                if (src.text != nullptr) {
+                    const u64 first_b = p_lo ? p_lo - 1 : 0;
+                    const uintptr_t a0 = ((uintptr_t)(src.text + first_b)) & ~(uintptr_t)3;
+                    const u64 t0 = (u64)(a0 - (uintptr_t)src.text);
+                    const u32 nq = (u32)((p_hi + 3 - t0) >> 2);
+                    const u32 *src32 = reinterpret_cast<const u32 *>(a0);
+                    for (u32 i = tid; i < nq && i < (u32)Smem::TMAX; i += THREADS) cp_async4(&sm.tst[s][i], src32 + i);
+                }
+            }
+            cp_async_commit();                                         // one group per tile, also when empty: wait_group counts groups
+        }
+    };
+
+    // ---- prologue: tile 0 of this CTA in flight, table entry of tile 1 fetched
+    u32 t = blockIdx.x;
+    uint2 ti_cur = make_uint2(0, 0), ti_next = make_uint2(0, 0);
+    if (SEG) {
+        if (t < ntickets) ti_cur = a.tinfo[t];
+        if (t + stride < ntickets && t + stride >= t) ti_next = a.tinfo[t + stride];
+    }
+    u64 lo = 0; u32 count = 0;
+    if (t < ntickets) { range_of(t, ti_cur, lo, count); issue(0, lo, count); }
+    u32 waited0 = 0, waited1 = 0;                                  // completed TMA phases per stage (only full, aligned tiles use TMA)
+
+    for (u32 it = 0; t < ntickets; ++it) {
+        const int s = (int)(it & 1);
+        const u32 par = (s ? waited1 : waited0) & 1;
+        // ---- next tile: its loads go into the other stage now; the table entry after it is fetched for the next iteration
+        const u32 tn = t + stride;
+        const bool have_next = tn < ntickets && tn > t;
+        u64 lo_n = 0; u32 count_n = 0;
+        uint2 ti_next2 = make_uint2(0, 0);
+        if (have_next) {
+            range_of(tn, ti_next, lo_n, count_n);
+            if (SEG && tn + stride < ntickets && tn + stride > tn) ti_next2 = a.tinfo[tn + stride];
+        }
+        if (have_next) issue(s ^ 1, lo_n, count_n);
+        else if (Src::kMode == SRC_KMER) cp_async_commit();            // keep one group per iteration
+
+        if (count != 0) {
+            const u32 segi = t % a.nseg, j = t / a.nseg;
+            const bool full = count == (u32)TILE;
+            if (tid < kRadixSize) sm.cnt[tid] = 0;
+            u64 gbase = 0;
+            if (tid < kRadixSize) {
+                if (SEG) gbase = (u64)a.boff[(segi << 8) + tid];
+                else { gbase = a.base[tid]; if (a.cp != nullptr) gbase += (u64)a.cp[(u64)segi * kRadixSize + tid]; }
+            }
+            u64 key[IPT];
+            const u32 wbase = warp * (IPT * 32) + lane;
+            bool bulk = false;
+            if constexpr (Src::kMode == SRC_KMER) {
+                cp_async_wait_group<1>();                              // everything but the newest group (the next tile) has landed
+                __syncthreads();
+                const u64 p_hi = src.n - 1 - lo, p_lo = p_hi - (count - 1);
+                const u64 w_lo = (p_lo * (u64)src.b) >> 6;
+                u64 w_hi = ((p_hi * (u64)src.b) >> 6) + 1;
+                if (w_hi > src.nwords - 1) w_hi = src.nwords - 1;
+                const u32 nw = (u32)(w_hi - w_lo + 1);
+                const u64 *sw = sm.wst[s];
+                const u8 *sb = reinterpret_cast<const u8 *>(sm.tst[s]);
+                u64 t0 = 0;
+                if (src.text != nullptr) {
+                    const u64 first_b = p_lo ? p_lo - 1 : 0;
+                    const uintptr_t a0 = ((uintptr_t)(src.text + first_b)) & ~(uintptr_t)3;
+                    t0 = (u64)(a0 - (uintptr_t)src.text);
+                }
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const u32 li = wbase + i * 32;
+                    u64 k = 0;
+                    if (full || li < count) {
+                        const u64 p = p_hi - li;
+                        const u64 bit = p * (u64)src.b;
+                        const u32 q = (u32)((bit >> 6) - w_lo); const int off = (int)(bit & 63);
+                        const u64 hi = sw[q], lw = sw[q + 1 < nw ? q + 1 : q];
+                        const u64 x = off ? ((hi << off) | (lw >> (64 - off))) : hi;
+                        k = (x >> (64 - src.K)) << src.key_shift;
+                        if (src.text != nullptr && p > 0) k |= (u64)sb[(p - 1) - t0];
+                    }
+                    key[i] = k;
+                }
+            } else {
+                bulk = full && a.use_bulk && ((lo * 4) & 15) == 0;
+                __syncthreads();                                       // cnt zeroed; previous tile's readers of this stage are long gone
+                if (bulk) {
+                    mbar_wait(&sm.mbar[s][0], par);
+#pragma unroll
+                    for (int i = 0; i < IPT; ++i) key[i] = sm.kst[s][wbase + i * 32];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < IPT; ++i) {
+                        const u32 li = wbase + i * 32;
+                        key[i] = (full || li < count) ? kin[lo + li] : 0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < IPT; ++i) {
+                        const u32 li = wbase + i * 32;
+                        if (full || li < count) sm.vst[s][li] = vin[lo + li];
+                    }
+                }
+            }
+
+            // ---- rank inside the tile: one shared atomic per element
+            u32 rk[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const u32 li = wbase + i * 32;
+                rk[i] = 0;
+                if (full || li < count) rk[i] = atomicAdd(&sm.cnt[digit_of(key[i], shift, dmask)], 1u);
+            }
+            __syncthreads();
+
+            // ---- per digit: publish the tile count, prefetch the look-back, exclusive scan of the counts
+            u32 cnt = 0, tileoff = 0;
+            LookState<ST> ls;
+            const u32 nseg = a.nseg;
+            if (tid < kRadixSize) {
+                cnt = sm.cnt[tid];
+                st_relaxed(status + (u64)t * kRadixSize + tid, j == 0 ? StWord<ST>::inc(cnt) : StWord<ST>::agg(cnt));
+#pragma unroll
+                for (int q = 0; q < kLookBatch; ++q)
+                    ls.w[q] = (u32)(q + 1) <= j ? ld_relaxed(status + (u64)(t - (u32)(q + 1) * nseg) * kRadixSize + tid) : StWord<ST>::inc(0);
+                u32 x = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+                if (lane == 31) sm.scan_tmp[warp] = x;
+                tileoff = x - cnt;
+            }
+            __syncthreads();
+            if (tid < kRadixSize) {
+#pragma unroll
+                for (int w = 0; w < kRadixSize / 32; ++w) if (w < warp) tileoff += sm.scan_tmp[w];
+                sm.tileoff[tid] = tileoff;
+            }
+            __syncthreads();
+
+            // ---- scatter into shared memory in digit order (the current stage's key area becomes the ordered tile)
+            u64 *skeys = sm.kst[Src::kMode == SRC_ARRAYS ? s : 0];
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const u32 li = wbase + i * 32;
+                if (full || li < count) {
+                    const u32 pos = sm.tileoff[digit_of(key[i], shift, dmask)] + rk[i];
+                    skeys[pos] = key[i];
+                    if constexpr (Src::kMode == SRC_KMER) sm.vals[pos] = (u32)(src.n - 1 - lo - li);
+                    else rk[i] = pos;
+                }
+            }
+            if constexpr (Src::kMode == SRC_ARRAYS) {
+                if (bulk) { mbar_wait(&sm.mbar[s][1], par); if (s) ++waited1; else ++waited0; }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const u32 li = wbase + i * 32;
+                    if (full || li < count) sm.vals[rk[i]] = sm.vst[s][li];
+                }
+            }
+
+            // ---- chained scan over the earlier tiles of this segment
+            if (tid < kRadixSize) {
+                u64 excl = 0;
+                if (j != 0) {
+                    bool done = false;
+#pragma unroll
+                    for (int q = 0; q < kLookBatch; ++q)
+                        if (!done) done = lookback_consume<ST>(ls.w[q], status, (i64)t - (i64)(q + 1) * nseg, (u32)tid, excl, a.err);
+                    u32 back = kLookBatch;
+                    while (!done) {
+                        ST w[kLookRefill];
+#pragma unroll
+                        for (int q = 0; q < kLookRefill; ++q) {
+                            const u32 k = back + 1 + q;
+                            w[q] = k <= j ? ld_relaxed(status + (u64)(t - k * nseg) * kRadixSize + tid) : StWord<ST>::inc(0);
+                        }
+#pragma unroll
+                        for (int q = 0; q < kLookRefill; ++q)
+                            if (!done) done = lookback_consume<ST>(w[q], status, (i64)t - (i64)(back + 1 + q) * nseg, (u32)tid, excl, a.err);
+                        back += kLookRefill;
+                    }
+                    st_relaxed(status + (u64)t * kRadixSize + tid, StWord<ST>::inc(excl + (u64)cnt));
+                }
+                sm.goff[tid] = gbase + excl - (u64)tileoff;
+            }
+            __syncthreads();
+
+            // ---- write out
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const u32 idx = i * THREADS + tid;
+                if (full || idx < count) {
+                    const u64 k = skeys[idx];
+                    const u64 g = sm.goff[digit_of(k, shift, dmask)] + idx;
+                    kout[g] = k;
+                    vout[g] = sm.vals[idx];
+                }
+            }
+        } else if (Src::kMode == SRC_KMER) {
+            cp_async_wait_group<1>();
+        }
+        __syncthreads();                                               // the stage, cnt, goff, vals are free for the next tile
+        t = tn; lo = lo_n; count = count_n; ti_next = ti_next2;
+        if (!have_next) break;
+    }
+    if (Src::kMode == SRC_KMER) cp_async_wait_group<0>();
+}
+
 // Ticket table of the segmented pass: ticket t = tile t / 256 of top-level bucket t % 256 -> (first element, count).
 static __global__ void __launch_bounds__(256)
 seg_tiles_kernel(const u32 *__restrict__ boff, const u32 *__restrict__ tstart, u32 tile, u32 grid, uint2 *__restrict__ tinfo)
@@ -349,6 +636,34 @@ static void launch_part_variant(Ctx &c, int kc, double algo_bytes, const Src &sr
         LSC_LAUNCH(c, kc, algo_bytes, kern, (u32)grid, THREADS, sizeof(Smem), kin, vin, kout, vout, a, (u64 *)status, src);
     }
 }
+
+// Persistent launch: grid = resident CTAs (occupancy * SMs), tickets 0..ntickets-1 are walked with a grid stride.
+template <typename ST, typename Src, bool SEG>
+static void launch_part_pipe_st(Ctx &c, int kc, double algo_bytes, const Src &src, const u64 *kin, const u32 *vin, u64 *kout, u32 *vout,
+                                const PartArgs &a, u64 ntickets, void *status)
+{
+    constexpr int THREADS = 384, IPT = 10;
+    constexpr int MINB = Src::kMode == SRC_KMER ? 3 : 2;
+    typedef PipeSmem<THREADS, IPT, Src::kMode> Smem;
+    auto kern = part_pipe_kernel<THREADS, IPT, MINB, ST, Src, SEG>;
+    c.check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, sizeof(Smem)) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    u64 grid = (u64)per_sm * c.sm_count;
+    if (grid > ntickets) grid = ntickets;
+    LSC_LAUNCH(c, kc, algo_bytes, kern, (u32)grid, THREADS, sizeof(Smem), kin, vin, kout, vout, a, (ST *)status, src, (u32)ntickets);
+}
+template <typename Src, bool SEG>
+static void launch_part_pipe(Ctx &c, int kc, double algo_bytes, const Src &src, const u64 *kin, const u32 *vin, u64 *kout, u32 *vout,
+                             PartArgs a, u64 ntickets, void *status)
+{
+    static const bool bulk_env = [] { const char *e = getenv("LIBSAIS_CUDA_TMA"); return !(e && *e && atoi(e) == 0); }();
+    a.use_bulk = bulk_env && Src::kMode == SRC_ARRAYS && (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0;
+    a.ticket = nullptr;
+    if (a.n < (1ull << 30)) launch_part_pipe_st<u32, Src, SEG>(c, kc, algo_bytes, src, kin, vin, kout, vout, a, ntickets, status);
+    else                    launch_part_pipe_st<u64, Src, SEG>(c, kc, algo_bytes, src, kin, vin, kout, vout, a, ntickets, status);
+}
+static const u32 kPipeTile = 384 * 10;
 
 // Launch one partition pass with `grid` tickets.  `status` must hold grid * 256 status words (u32 when
 // a.n < 2^30, else u64), zeroed; a.ticket one zeroed u32.
