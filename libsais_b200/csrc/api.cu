@@ -315,12 +315,15 @@ IDX unbwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, const IDX *f
     for (IDX t = 0; t <= (n - 1) / r; ++t) if (I[t] <= 0 || I[t] > n) return -1;
     if (!c || !c->ok || (u64)n > kMaxN) return -2;
     Call call(*c);
-    if (!c->reserve((size_t)n * 2 + kPad + unbwt_workspace_bytes((u64)n) + 8192)) return -2;
+    const u64 n_aux = r < n ? ((u64)n - 1) / (u64)r + 1 : 0;        // r == n: only the primary index is known
+    if (!c->reserve((size_t)n * 2 + kPad + unbwt_workspace_bytes((u64)n) + n_aux * 12 + 8192)) return -2;
     const u8 *d_B = (const u8 *)upload_text(*c, T, (size_t)n);
     u8 *d_U = c->alloc_n<u8>((size_t)n);
     if (!d_B || !d_U) return -2;
+    const u32 *d_I = nullptr;
+    if (n_aux >= 2) { d_I = upload_indexes<IDX>(*c, I, n_aux); if (!d_I) return -2; }
     call.start_timer();
-    if (run_unbwt(*c, d_B, d_U, (u64)n, (u64)I[0]) != 0) return -2;
+    if (run_unbwt(*c, d_B, d_U, (u64)n, (u64)I[0], n_aux >= 2 ? (u64)r : 0, d_I, n_aux) != 0) return -2;
     call.stop_timer();
     if (!copy_d2h(*c, U, d_U, (size_t)n)) return -2;
     if (!call.finish()) return -2;

@@ -57,7 +57,7 @@ int run_plcp(Ctx &c, const void *d_T, int sym_bytes, const u32 *d_SA, u32 *d_PLC
 int run_lcp(Ctx &c, const u32 *d_PLCP, const u32 *d_SA, u32 *d_LCP, u64 n);
 //   unbwt: text U[n] from BWT B[n] and the primary index
 size_t unbwt_workspace_bytes(u64 n);
-int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary);
+int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary, u64 aux_r = 0, const u32 *d_I = nullptr, u64 n_aux = 0);   // d_I: aux samples (row of suffix j * aux_r)
 
 // generalized suffix arrays: integer text with one distinct symbol per separator (gsa.cu)
 size_t gsa_workspace_bytes(u64 n);

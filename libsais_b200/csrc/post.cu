@@ -335,6 +335,28 @@ unbwt_walk2_kernel(const u32 *__restrict__ psi, const u64 *__restrict__ base, u6
     } while (!unbwt_stop(x, smask, primary) && steps <= n);
 }
 
+// aux samples hand every r-th text position its row for free (I[j] = row of suffix j*r, reference src/libsais.c:7943-7973 decodes
+// the blocks independently too): chain j starts at row I[j] and emits U[j*r .. j*r + r) -- one walk, no list ranking
+__global__ void __launch_bounds__(128)
+unbwt_walk_aux_kernel(const u32 *__restrict__ psi, const u64 *__restrict__ base, u64 n, u64 r, const u32 *__restrict__ I, u64 nchains, u8 *__restrict__ U)
+{
+    __shared__ u64 cum[257];
+    for (int i = threadIdx.x; i < 256; i += 128) cum[i] = base[i] + 1;
+    if (threadIdx.x == 0) cum[256] = n + 1;
+    __syncthreads();
+    const u64 j = (u64)blockIdx.x * 128 + threadIdx.x;
+    if (j >= nchains) return;
+    u64 x = I[j];
+    const u64 t0 = j * r, t1 = t0 + r < n ? t0 + r : n;
+    for (u64 t = t0; t < t1; ++t) {
+        if (x > n) return;                               // inconsistent samples: never read out of bounds
+        int lo = 0, hi = 256;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (cum[mid] <= x) lo = mid; else hi = mid; }
+        U[t] = (u8)lo;
+        x = psi[x];
+    }
+}
+
 static int unbwt_log_s(u64 n) { return n >= (1ull << 24) ? 7 : 5; }
 
 size_t unbwt_workspace_bytes(u64 n)
@@ -343,7 +365,7 @@ size_t unbwt_workspace_bytes(u64 n)
     return (size_t)n * (4 + 4 + 1) + 8 + RadixSort<u8, u32>::temp_bytes(n) + ns * (4 + 4 + 4 + 8 + 8) + 16 * 256;
 }
 
-int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary)
+int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary, u64 aux_r, const u32 *d_I, u64 n_aux)
 {
     const int logS = unbwt_log_s(n);
     const u64 nsplit = (n >> logS) + 1;
@@ -364,6 +386,11 @@ int run_unbwt(Ctx &c, const u8 *d_B, u8 *d_U, u64 n, u64 primary)
     if (where != 1) return -2;
     const u64 *base = (const u64 *)((char *)temp + kMaxPasses * kRadixSize * sizeof(u64));
 
+    // with dense enough aux samples every block is an independent chain (enough chains to hide the dependent loads)
+    if (d_I != nullptr && aux_r >= 2 && n_aux >= 2 && (aux_r <= 512 || n_aux >= 200000 || n < ((u64)1 << 20))) {
+        LSC_LAUNCH(c, KC_UNBWT_WALK, (double)n * 5, unbwt_walk_aux_kernel, (u32)ceil_div(n_aux, 128), 128, 0, psi, base, n, aux_r, d_I, n_aux, d_U);
+        return c.failed() ? -2 : 0;
+    }
     LSC_LAUNCH(c, KC_UNBWT_WALK, (double)n * 4, unbwt_walk1_kernel, (u32)ceil_div(nsplit, 128), 128, 0,
                psi, n, primary, logS, nsplit, nxt0, len);
     LSC_LAUNCH(c, KC_UNBWT_RANK, (double)nsplit * 12, unbwt_dist_init_kernel, (u32)ceil_div(nsplit, 256), 256, 0, len, dist0, nsplit);

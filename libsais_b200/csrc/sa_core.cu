@@ -798,7 +798,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     // Measured on B200 (profiles/part_pass_r2.md): it pays for the array source (TMA prefetch: 2.15 -> 1.99 ms) and not for the
     // k-mer source (cp.async staging costs more issue slots than it hides: 1.73 -> 2.05 ms), hence the default 2.
     static const int pipe_env = [] { const char *e = getenv("LIBSAIS_CUDA_PART_PIPE"); return (e && *e) ? atoi(e) : 2; }();
-    const u32 ptile = pipe_env ? kPipeTile : part_tile();
+    const int pipe = part_tile() == kPipeTile ? pipe_env : 0;       // both kernels of a run must agree on the tile (chunk / cell grid)
+    const u32 ptile = part_tile();
     const u64 nt1 = ceil_div(n, (u64)ptile);
     u64 want_seg = 16;                                                              // chunks of the first pass (profiles/part_pass_r2.md)
     { const char *env = getenv("LIBSAIS_CUDA_PART_NSEG"); if (env && *env && atoi(env) > 0) want_seg = (u64)atoi(env); }
@@ -860,13 +861,13 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         pa.shift = key_shift + K - 8; pa.base = m_base; pa.cp = m_H; pa.nseg = nseg1; pa.tpc = tpc; pa.boff = nullptr; pa.tstart = nullptr; pa.tinfo = nullptr;
         pa.ticket = atomic_tickets ? tickets : nullptr;
         c.check(cudaMemsetAsync(status, 0, grid1 * kRadixSize * stw, st));
-        if (pipe_env & 1) launch_part_pipe<KmerSrc, false>(c, KC_SORT_PASS_GEN, (double)n * (2.0 + 12.0), src, (const u64 *)nullptr, (const u32 *)nullptr, keyA, valA, pa, grid1, status);
+        if (pipe & 1) launch_part_pipe<KmerSrc, false>(c, KC_SORT_PASS_GEN, (double)n * (2.0 + 12.0), src, (const u64 *)nullptr, (const u32 *)nullptr, keyA, valA, pa, grid1, status);
         else launch_part_pass<u64, u32, KmerSrc, false>(c, KC_SORT_PASS_GEN, (double)n * (2.0 + 12.0), src, (const u64 *)nullptr, (const u32 *)nullptr, keyA, valA, pa, grid1, status);
         pa.shift = key_shift + K - 16; pa.base = nullptr; pa.cp = nullptr; pa.nseg = kRadixSize; pa.tpc = 0; pa.boff = m_boff; pa.tstart = m_tstart; pa.tinfo = tinfo;
         pa.ticket = atomic_tickets ? tickets + 1 : nullptr;
         LSC_LAUNCH(c, KC_SORT_HIST, 0.0, seg_tiles_kernel, (u32)ceil_div(grid2, 256), 256, 0, m_boff, m_tstart, ptile, (u32)grid2, tinfo);
         c.check(cudaMemsetAsync(status, 0, grid2 * kRadixSize * stw, st));
-        if (pipe_env & 2) launch_part_pipe<ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
+        if (pipe & 2) launch_part_pipe<ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
         else launch_part_pass<u64, u32, ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
         LSC_LAUNCH(c, KC_SORT_HIST, 0.0, bucket_tiles_kernel, (u32)ceil_div(btiles, 256), 256, 0, m_boff, btiles, Cw, tb);
         c.check(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));

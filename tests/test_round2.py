@@ -210,3 +210,24 @@ def test_distributed_bwt_through_libsais64_bwt(cu):
                 assert gi[0] == want[0] and (gi[1] == want[1]).all()
     finally:
         os.environ.pop("LIBSAIS_CUDA_DIST", None)
+
+
+def test_unbwt_aux_uses_the_samples(cu):
+    """libsais_unbwt_aux decodes every block of r symbols as an independent chain that starts at the sampled row I[j]
+    (reference src/libsais.c:7943-7973 decodes the blocks independently too).  Parity on several r, sizes that are not
+    multiples of r, both index widths; and a proof that the samples are really what drives the decoding: with I[1] and I[2]
+    exchanged the output has exactly those two blocks exchanged."""
+    o = _best_cpu()
+    for T in (gen.dna(21, 100_000), gen.rand_bytes(22, 65_537), gen.repetitive_dna(2_000, 30), np.zeros(5_000, dtype=np.uint8)):
+        for r in (2, 64, 256, 4096):
+            for bits in (32, 64):
+                rc, U, I = o.bwt_aux(T, r, bits)
+                got = cu.unbwt_aux(U, r, I, bits)
+                assert got[0] == 0 and (got[1] == T).all(), (len(T), r, bits)
+    T = gen.dna(23, 10 * 256)
+    r = 256
+    rc, U, I = o.bwt_aux(T, r)
+    J = I.copy(); J[1], J[2] = I[2], I[1]
+    got = cu.unbwt_aux(U, r, J)
+    want = T.copy(); want[r:2 * r], want[2 * r:3 * r] = T[2 * r:3 * r], T[r:2 * r]
+    assert got[0] == 0 and (got[1] == want).all()
