@@ -410,7 +410,8 @@ def run_c4(args, ctx, dev, local, rank, world, dist, barrier, sampler=None, reps
     from libsais_b200 import gen
     lib = libsais_b200.load_library()
     nblk, n = args.c4_blocks, args.c4_block_bytes
-    mine = list(range(rank, nblk, world))
+    from libsais_b200 import sharding
+    mine = sharding.blocks_for_rank(nblk, rank, world)          # block b -> rank b mod world (tests/test_sharding.py covers it on gloo)
     k = len(mine)
     # inputs: generated on the device (numpy needs ~2 s per block), resident copy + pinned host copy
     dT = torch.empty((k, n), dtype=torch.uint8, device=dev)

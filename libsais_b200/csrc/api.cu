@@ -20,6 +20,8 @@
 #include "../../include/libsais.h"
 #include "../../include/libsais64.h"
 #include "../../include/libsais_cuda.h"
+#include "../../include/libsais16.h"
+#include "../../include/libsais16x64.h"
 
 using namespace lsc;
 
@@ -369,6 +371,158 @@ IDX lcp_body(Ctx *c, const IDX *PLCP, const IDX *SA, IDX *LCP, IDX n)
     if (run_lcp(*c, d_P, d_SA, d_L, (u64)n) != 0) return -2;
     call.stop_timer();
     if (!download_indexes<IDX>(*c, d_L, LCP, (u64)n, wide)) return -2;   // LCP may alias SA: SA was consumed above
+    if (!call.finish()) return -2;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// 16-bit symbols (reference include/libsais16.h, include/libsais16x64.h; src/libsais16.c:6995 ff.): the SA and PLCP cores run on
+// the text widened to 32-bit symbols on the device; BWT rows are gathered from the suffix array; the inverse BWT handles
+// the 65536-symbol alphabet (post.cu).  Validation and fast paths mirror the 8-bit bodies above.
+// ------------------------------------------------------------------------------------------
+template <typename IDX> void host_freq16(const uint16_t *T, IDX n, IDX *freq)
+{
+    if (!freq) return;
+    for (int s = 0; s < 65536; ++s) freq[s] = 0;
+    for (IDX i = 0; i < n; ++i) freq[T[i]]++;
+}
+template <typename IDX> bool download_freq16(Ctx &c, const u64 *d_hist, IDX *freq)
+{
+    std::vector<u64> h(65536);
+    if (!copy_d2h(c, h.data(), d_hist, 65536 * sizeof(u64)) || !c.sync()) return false;
+    for (int s = 0; s < 65536; ++s) freq[s] = (IDX)h[s];
+    return true;
+}
+
+// device text of a uint16_t host text: the raw symbols and the widened (or, for GSA, separator-ranked) 32-bit text
+struct Text16 { const uint16_t *raw = nullptr; const u32 *wide = nullptr; };
+bool upload_text16(Ctx &c, const uint16_t *T, u64 n, bool gsa, Text16 *out)
+{
+    const uint16_t *d16 = (const uint16_t *)upload_text(c, T, (size_t)n * 2);
+    if (!d16) return false;
+    out->raw = d16;
+    if (gsa) {
+        out->wide = build_gsa_text16(c, d16, n);
+        return out->wide != nullptr;
+    }
+    u32 *w = (u32 *)c.alloc((size_t)n * 4 + kPad);
+    if (!w) return false;
+    c.check(cudaMemsetAsync((char *)w + (size_t)n * 4, 0, kPad, c.stream));
+    run_widen16(c, d16, w, n);
+    out->wide = w;
+    return true;
+}
+
+template <typename IDX>
+IDX sa16_body(Ctx *c, const uint16_t *T, IDX *SA, IDX n, IDX fs, IDX *freq, bool gsa)
+{
+    if (T == nullptr || SA == nullptr || n < 0 || fs < 0 || (gsa && n > 0 && T[n - 1] != 0)) return -1;
+    if (n < 2) { host_freq16(T, n, freq); if (n == 1) SA[0] = 0; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN - 512) return -2;
+    Call call(*c);
+    if (!c->reserve((size_t)n * 2 + kPad * 2 + (size_t)n * 4 + 65536 * 8 + gsa_workspace_bytes((u64)n) + sa_workspace_bytes((u64)n, 4) + 16384)) return -2;
+    Text16 t;
+    u64 *d_hist = freq ? c->alloc_n<u64>(65536) : nullptr;
+    if (freq && !d_hist) return -2;
+    if (!upload_text16(*c, T, (u64)n, gsa, &t)) return -2;
+    call.start_timer();
+    if (freq) run_hist_u16(*c, t.raw, (u64)n, d_hist);
+    if (gsa) {      // empty members are rejected like the reference does
+        c->check(cudaMemcpyAsync(c->h_scalars + S_GSA_INVALID, c->d_scalars + S_GSA_INVALID, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        if (!c->sync()) return -2;
+        if (c->h_scalars[S_GSA_INVALID] != 0) return -1;
+    }
+    SAResult res; SAOptions opt;
+    if (build_sa(*c, t.wide, 4, (u64)n, opt, &res) != 0) return -2;
+    call.stop_timer();
+    if (!download_indexes<IDX>(*c, res.SA, SA, (u64)n, res.scratch)) return -2;
+    if (freq && !download_freq16(*c, d_hist, freq)) return -2;
+    if (!call.finish()) return -2;
+    return 0;
+}
+
+template <typename IDX>
+IDX bwt16_body(Ctx *c, const uint16_t *T, uint16_t *U, IDX *A, IDX n, IDX fs, IDX *freq, IDX r, IDX *I, bool aux)
+{
+    if (T == nullptr || U == nullptr || A == nullptr || n < 0 || fs < 0) return -1;
+    if (aux && (r < 2 || (r & (r - 1)) != 0 || I == nullptr)) return -1;
+    if (n <= 1) {
+        host_freq16(T, n, freq);
+        if (n == 1) U[0] = T[0];
+        if (aux) { I[0] = n; return 0; }
+        return n;
+    }
+    if (!c || !c->ok || (u64)n > kMaxN - 512) return -2;
+    Call call(*c);
+    const u64 n_aux = aux ? ((u64)n - 1) / (u64)r + 1 : 0;
+    if (!c->reserve((size_t)n * 4 + kPad * 2 + (size_t)n * 4 + 65536 * 8 + n_aux * 4 + sa_workspace_bytes((u64)n, 4) + 16384)) return -2;
+    Text16 t;
+    u64 *d_hist = freq ? c->alloc_n<u64>(65536) : nullptr;
+    uint16_t *d_U = c->alloc_n<uint16_t>((size_t)n);
+    u32 *d_I = n_aux ? c->alloc_n<u32>(n_aux) : nullptr;
+    if ((freq && !d_hist) || !d_U || (n_aux && !d_I)) return -2;
+    if (!upload_text16(*c, T, (u64)n, false, &t)) return -2;
+    call.start_timer();
+    if (freq) run_hist_u16(*c, t.raw, (u64)n, d_hist);
+    SAResult res; SAOptions opt;
+    if (build_sa(*c, t.wide, 4, (u64)n, opt, &res) != 0) return -2;
+    u64 primary = 0;
+    if (run_bwt16(*c, t.raw, res.SA, d_U, (u64)n, aux ? (u64)r : 0, d_I, &primary) != 0) return -2;
+    call.stop_timer();
+    if (!copy_d2h(*c, U, d_U, (size_t)n * 2)) return -2;
+    if (n_aux && !download_indexes<IDX>(*c, d_I, I, n_aux, res.scratch)) return -2;
+    if (freq && !download_freq16(*c, d_hist, freq)) return -2;
+    if (!call.finish()) return -2;
+    return aux ? 0 : (IDX)primary;
+}
+
+template <typename IDX>
+IDX unbwt16_body(Ctx *c, const uint16_t *T, uint16_t *U, IDX *A, IDX n, const IDX *freq, IDX r, const IDX *I)
+{
+    (void)freq;
+    if (T == nullptr || U == nullptr || A == nullptr || n < 0 || I == nullptr) return -1;
+    if (r != n && (r < 2 || (r & (r - 1)) != 0)) return -1;
+    if (n <= 1) {
+        if (I[0] != n) return -1;
+        if (n == 1) U[0] = T[0];
+        return 0;
+    }
+    for (IDX t = 0; t <= (n - 1) / r; ++t) if (I[t] <= 0 || I[t] > n) return -1;
+    if (!c || !c->ok || (u64)n > kMaxN) return -2;
+    Call call(*c);
+    const u64 n_aux = r < n ? ((u64)n - 1) / (u64)r + 1 : 0;
+    if (!c->reserve((size_t)n * 4 + kPad + unbwt16_workspace_bytes((u64)n) + n_aux * 12 + 8192)) return -2;
+    uint16_t *d_B = (uint16_t *)upload_text(*c, T, (size_t)n * 2);
+    uint16_t *d_U = c->alloc_n<uint16_t>((size_t)n);
+    if (!d_B || !d_U) return -2;
+    const u32 *d_I = nullptr;
+    if (n_aux >= 2) { d_I = upload_indexes<IDX>(*c, I, n_aux); if (!d_I) return -2; }
+    call.start_timer();
+    if (run_unbwt16(*c, d_B, d_U, (u64)n, (u64)I[0], n_aux >= 2 ? (u64)r : 0, d_I, n_aux) != 0) return -2;
+    call.stop_timer();
+    if (!copy_d2h(*c, U, d_U, (size_t)n * 2)) return -2;
+    if (!call.finish()) return -2;
+    return 0;
+}
+
+template <typename IDX>
+IDX plcp16_body(Ctx *c, const uint16_t *T, const IDX *SA, IDX *PLCP, IDX n, bool gsa)
+{
+    if (T == nullptr || SA == nullptr || PLCP == nullptr || n < 0 || (gsa && n > 0 && T[n - 1] != 0)) return -1;
+    if (n <= 1) { if (n == 1) PLCP[0] = 0; return 0; }
+    if (!c || !c->ok || (u64)n > kMaxN - 512) return -2;
+    Call call(*c);
+    if (!c->reserve((size_t)n * 2 + kPad * 2 + gsa_workspace_bytes((u64)n) + (size_t)n * (4 + 4 + 4 + 8 + 8) + plcp_workspace_bytes((u64)n) + 16384)) return -2;
+    Text16 t;
+    if (!upload_text16(*c, T, (u64)n, gsa, &t)) return -2;
+    u32 *d_SA = upload_indexes<IDX>(*c, SA, (u64)n);
+    u32 *d_P = c->alloc_n<u32>((size_t)n);
+    void *wide = sizeof(IDX) == 8 ? c->alloc((size_t)n * 8) : nullptr;
+    if (!d_SA || !d_P || (sizeof(IDX) == 8 && !wide)) return -2;
+    call.start_timer();
+    if (run_plcp(*c, t.wide, 4, d_SA, d_P, (u64)n) != 0) return -2;
+    call.stop_timer();
+    if (!download_indexes<IDX>(*c, d_P, PLCP, (u64)n, wide)) return -2;
     if (!call.finish()) return -2;
     return 0;
 }
@@ -849,5 +1003,68 @@ int64_t libsais_cuda_dist_partition_dev(const void *ctx, uint64_t *d_keys, uint3
     for (int r = 0; r <= nsplit && r < 65; ++r) counts_out[r] = counts[r];
     return rc == 0 && call.finish() ? 0 : (rc == -1 ? -1 : -2);
 }
+
+// ------------------------------------------------------------------ libsais16 / libsais16x64 (16-bit symbols)
+void *libsais16_create_ctx(void) { return new_ctx(-1); }
+void *libsais16_create_ctx_omp(int32_t threads) { return threads < 0 ? nullptr : new_ctx(-1); }
+void libsais16_free_ctx(void *ctx) { libsais_free_ctx(ctx); }
+void *libsais16_unbwt_create_ctx(void) { return new_ctx(-1); }
+void *libsais16_unbwt_create_ctx_omp(int32_t threads) { return threads < 0 ? nullptr : new_ctx(-1); }
+void libsais16_unbwt_free_ctx(void *ctx) { libsais_free_ctx(ctx); }
+
+#define LSC16(IDX, P)                                                                                                                      \
+    IDX P(const uint16_t *T, IDX *SA, IDX n, IDX fs, IDX *freq) { return sa16_body<IDX>(default_ctx(), T, SA, n, fs, freq, false); }       \
+    IDX P##_gsa(const uint16_t *T, IDX *SA, IDX n, IDX fs, IDX *freq) { return sa16_body<IDX>(default_ctx(), T, SA, n, fs, freq, true); } \
+    IDX P##_omp(const uint16_t *T, IDX *SA, IDX n, IDX fs, IDX *freq, IDX threads)                                                         \
+    { if (threads < 0) return -1; return sa16_body<IDX>(default_ctx(), T, SA, n, fs, freq, false); }                                       \
+    IDX P##_gsa_omp(const uint16_t *T, IDX *SA, IDX n, IDX fs, IDX *freq, IDX threads)                                                     \
+    { if (threads < 0) return -1; return sa16_body<IDX>(default_ctx(), T, SA, n, fs, freq, true); }                                        \
+    IDX P##_bwt(const uint16_t *T, uint16_t *U, IDX *A, IDX n, IDX fs, IDX *freq)                                                          \
+    { return bwt16_body<IDX>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }                                                    \
+    IDX P##_bwt_aux(const uint16_t *T, uint16_t *U, IDX *A, IDX n, IDX fs, IDX *freq, IDX r, IDX *I)                                       \
+    { return bwt16_body<IDX>(default_ctx(), T, U, A, n, fs, freq, r, I, true); }                                                           \
+    IDX P##_bwt_omp(const uint16_t *T, uint16_t *U, IDX *A, IDX n, IDX fs, IDX *freq, IDX threads)                                         \
+    { if (threads < 0) return -1; return bwt16_body<IDX>(default_ctx(), T, U, A, n, fs, freq, 0, nullptr, false); }                        \
+    IDX P##_bwt_aux_omp(const uint16_t *T, uint16_t *U, IDX *A, IDX n, IDX fs, IDX *freq, IDX r, IDX *I, IDX threads)                      \
+    { if (threads < 0) return -1; return bwt16_body<IDX>(default_ctx(), T, U, A, n, fs, freq, r, I, true); }                               \
+    IDX P##_unbwt(const uint16_t *T, uint16_t *U, IDX *A, IDX n, const IDX *freq, IDX i)                                                   \
+    { return unbwt16_body<IDX>(default_ctx(), T, U, A, n, freq, n, &i); }                                                                  \
+    IDX P##_unbwt_aux(const uint16_t *T, uint16_t *U, IDX *A, IDX n, const IDX *freq, IDX r, const IDX *I)                                 \
+    { return unbwt16_body<IDX>(default_ctx(), T, U, A, n, freq, r, I); }                                                                   \
+    IDX P##_unbwt_omp(const uint16_t *T, uint16_t *U, IDX *A, IDX n, const IDX *freq, IDX i, IDX threads)                                  \
+    { if (threads < 0) return -1; return unbwt16_body<IDX>(default_ctx(), T, U, A, n, freq, n, &i); }                                      \
+    IDX P##_unbwt_aux_omp(const uint16_t *T, uint16_t *U, IDX *A, IDX n, const IDX *freq, IDX r, const IDX *I, IDX threads)                \
+    { if (threads < 0) return -1; return unbwt16_body<IDX>(default_ctx(), T, U, A, n, freq, r, I); }                                       \
+    IDX P##_plcp(const uint16_t *T, const IDX *SA, IDX *PLCP, IDX n) { return plcp16_body<IDX>(default_ctx(), T, SA, PLCP, n, false); }    \
+    IDX P##_plcp_gsa(const uint16_t *T, const IDX *SA, IDX *PLCP, IDX n) { return plcp16_body<IDX>(default_ctx(), T, SA, PLCP, n, true); } \
+    IDX P##_lcp(const IDX *PLCP, const IDX *SA, IDX *LCP, IDX n) { return lcp_body<IDX>(default_ctx(), PLCP, SA, LCP, n); }                \
+    IDX P##_plcp_omp(const uint16_t *T, const IDX *SA, IDX *PLCP, IDX n, IDX threads)                                                      \
+    { if (threads < 0) return -1; return plcp16_body<IDX>(default_ctx(), T, SA, PLCP, n, false); }                                         \
+    IDX P##_plcp_gsa_omp(const uint16_t *T, const IDX *SA, IDX *PLCP, IDX n, IDX threads)                                                  \
+    { if (threads < 0) return -1; return plcp16_body<IDX>(default_ctx(), T, SA, PLCP, n, true); }                                          \
+    IDX P##_lcp_omp(const IDX *PLCP, const IDX *SA, IDX *LCP, IDX n, IDX threads)                                                          \
+    { if (threads < 0) return -1; return lcp_body<IDX>(default_ctx(), PLCP, SA, LCP, n); }
+LSC16(int32_t, libsais16)
+LSC16(int64_t, libsais16x64)
+#undef LSC16
+
+int32_t libsais16_int(int32_t *T, int32_t *SA, int32_t n, int32_t k, int32_t fs) { return sa_int_body<int32_t, int32_t>(default_ctx(), T, SA, n, k, fs); }
+int32_t libsais16_int_omp(int32_t *T, int32_t *SA, int32_t n, int32_t k, int32_t fs, int32_t threads)
+{ if (threads < 0) return -1; return sa_int_body<int32_t, int32_t>(default_ctx(), T, SA, n, k, fs); }
+int64_t libsais16x64_long(int64_t *T, int64_t *SA, int64_t n, int64_t k, int64_t fs) { return sa_int_body<int64_t, int64_t>(default_ctx(), T, SA, n, k, fs); }
+int64_t libsais16x64_long_omp(int64_t *T, int64_t *SA, int64_t n, int64_t k, int64_t fs, int64_t threads)
+{ if (threads < 0) return -1; return sa_int_body<int64_t, int64_t>(default_ctx(), T, SA, n, k, fs); }
+int32_t libsais16_ctx(const void *ctx, const uint16_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq)
+{ if (ctx == nullptr) return -1; return sa16_body<int32_t>(as_ctx(ctx), T, SA, n, fs, freq, false); }
+int32_t libsais16_gsa_ctx(const void *ctx, const uint16_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq)
+{ if (ctx == nullptr) return -1; return sa16_body<int32_t>(as_ctx(ctx), T, SA, n, fs, freq, true); }
+int32_t libsais16_bwt_ctx(const void *ctx, const uint16_t *T, uint16_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq)
+{ if (ctx == nullptr) return -1; return bwt16_body<int32_t>(as_ctx(ctx), T, U, A, n, fs, freq, 0, nullptr, false); }
+int32_t libsais16_bwt_aux_ctx(const void *ctx, const uint16_t *T, uint16_t *U, int32_t *A, int32_t n, int32_t fs, int32_t *freq, int32_t r, int32_t *I)
+{ if (ctx == nullptr) return -1; return bwt16_body<int32_t>(as_ctx(ctx), T, U, A, n, fs, freq, r, I, true); }
+int32_t libsais16_unbwt_ctx(const void *ctx, const uint16_t *T, uint16_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t i)
+{ if (ctx == nullptr) return -1; return unbwt16_body<int32_t>(as_ctx(ctx), T, U, A, n, freq, n, &i); }
+int32_t libsais16_unbwt_aux_ctx(const void *ctx, const uint16_t *T, uint16_t *U, int32_t *A, int32_t n, const int32_t *freq, int32_t r, const int32_t *I)
+{ if (ctx == nullptr) return -1; return unbwt16_body<int32_t>(as_ctx(ctx), T, U, A, n, freq, r, I); }
 
 }  // extern "C"

@@ -89,6 +89,15 @@ void run_rank_scan(Ctx &c, u32 *tagg, u64 ntiles, u64 *out_counts);
 int sa64_multi(const u8 *T, i64 *SA, u64 n, i64 *freq, const int *devices, int ndev, void *stats /* libsais_cuda_dist_stats, nullable */);
 i64 bwt64_multi(const u8 *T, u8 *U, i64 *A, u64 n, i64 *freq, u64 aux_r, i64 *aux_I, const int *devices, int ndev);
 
+// 16-bit symbols (post.cu, gsa.cu): widened text for the SA / PLCP cores, 65536-bin frequencies, BWT rows from the SA,
+// inverse BWT over a 65536-symbol alphabet
+void run_widen16(Ctx &c, const uint16_t *src, u32 *dst, u64 n);
+void run_hist_u16(Ctx &c, const uint16_t *d_T, u64 n, u64 *d_hist /* 65536 */);
+int run_bwt16(Ctx &c, const uint16_t *d_T, const u32 *d_SA, uint16_t *d_U, u64 n, u64 aux_r, u32 *d_I, u64 *primary_out);
+size_t unbwt16_workspace_bytes(u64 n);
+int run_unbwt16(Ctx &c, uint16_t *d_B /* clobbered */, uint16_t *d_U, u64 n, u64 primary, u64 aux_r, const u32 *d_I, u64 n_aux);
+u32 *build_gsa_text16(Ctx &c, const uint16_t *d_T, u64 n);
+
 // conversions used by the 64-bit API
 void run_widen(Ctx &c, const u32 *src, i64 *dst, u64 n);
 void run_narrow(Ctx &c, const i64 *src, u32 *dst, u64 n);

@@ -14,8 +14,9 @@ static const int kSepThreads = 256;
 static const int kSepPerThread = 16;
 static const int kSepTile = kSepThreads * kSepPerThread;
 
+template <typename SymT>
 __global__ void __launch_bounds__(kSepThreads)
-sep_count_kernel(const u8 *__restrict__ T, u64 n, u32 *__restrict__ tile_counts, u64 *__restrict__ invalid)
+sep_count_kernel(const SymT *__restrict__ T, u64 n, u32 *__restrict__ tile_counts, u64 *__restrict__ invalid)
 {
     __shared__ u32 s_w[kSepThreads / 32];
     const u64 base = (u64)blockIdx.x * kSepTile + (u64)threadIdx.x * kSepPerThread;
@@ -71,17 +72,18 @@ sep_scan_kernel(u32 *__restrict__ v, u64 count, u64 *__restrict__ total)
     }
 }
 
+template <typename SymT>
 __global__ void __launch_bounds__(kSepThreads)
-sep_apply_kernel(const u8 *__restrict__ T, u64 n, const u32 *__restrict__ tile_excl, const u64 *__restrict__ total,
+sep_apply_kernel(const SymT *__restrict__ T, u64 n, const u32 *__restrict__ tile_excl, const u64 *__restrict__ total,
                  u32 *__restrict__ Tint)
 {
     __shared__ u32 s_w[kSepThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 base = (u64)blockIdx.x * kSepTile + (u64)threadIdx.x * kSepPerThread;
-    u8 b[kSepPerThread];
+    SymT b[kSepPerThread];
     u32 c = 0;
 #pragma unroll
-    for (int i = 0; i < kSepPerThread; ++i) { b[i] = base + i < n ? T[base + i] : (u8)1; c += b[i] == 0 ? 1u : 0u; }
+    for (int i = 0; i < kSepPerThread; ++i) { b[i] = base + i < n ? T[base + i] : (SymT)1; c += b[i] == 0 ? 1u : 0u; }
     u32 inc = c;
     for (int off = 1; off < 32; off <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
     if (lane == 31) s_w[warp] = inc;
@@ -97,7 +99,8 @@ sep_apply_kernel(const u8 *__restrict__ T, u64 n, const u32 *__restrict__ tile_e
 size_t gsa_workspace_bytes(u64 n) { return (size_t)n * 4 + ceil_div(n, kSepTile) * 4 + 1024; }
 
 // T' (u32[n] + 64 bytes of zero padding for the PLCP compare) in the ctx arena; returns nullptr on failure.
-u32 *build_gsa_text(Ctx &c, const u8 *d_T, u64 n)
+template <typename SymT>
+static u32 *build_gsa_text_t(Ctx &c, const SymT *d_T, u64 n)
 {
     const u64 tiles = ceil_div(n, kSepTile);
     u32 *Tint = (u32 *)c.alloc((size_t)n * 4 + 64);
@@ -106,10 +109,13 @@ u32 *build_gsa_text(Ctx &c, const u8 *d_T, u64 n)
     u64 *total = c.d_scalars + S_GSA_TOTAL;
     c.check(cudaMemsetAsync((char *)Tint + (size_t)n * 4, 0, 64, c.stream));
     c.check(cudaMemsetAsync(c.d_scalars + S_GSA_INVALID, 0, sizeof(u64), c.stream));
-    LSC_LAUNCH(c, KC_CONVERT, (double)n, sep_count_kernel, (u32)tiles, kSepThreads, 0, d_T, n, counts, c.d_scalars + S_GSA_INVALID);
+    LSC_LAUNCH(c, KC_CONVERT, (double)n * sizeof(SymT), sep_count_kernel<SymT>, (u32)tiles, kSepThreads, 0, d_T, n, counts, c.d_scalars + S_GSA_INVALID);
     LSC_LAUNCH(c, KC_CONVERT, (double)tiles * 8, sep_scan_kernel, 1, 1024, 0, counts, tiles, total);
-    LSC_LAUNCH(c, KC_CONVERT, (double)n * 5, sep_apply_kernel, (u32)tiles, kSepThreads, 0, d_T, n, counts, total, Tint);
+    LSC_LAUNCH(c, KC_CONVERT, (double)n * (4 + sizeof(SymT)), sep_apply_kernel<SymT>, (u32)tiles, kSepThreads, 0, d_T, n, counts, total, Tint);
     return c.failed() ? nullptr : Tint;
 }
+
+u32 *build_gsa_text(Ctx &c, const u8 *d_T, u64 n) { return build_gsa_text_t<u8>(c, d_T, n); }
+u32 *build_gsa_text16(Ctx &c, const uint16_t *d_T, u64 n) { return build_gsa_text_t<uint16_t>(c, d_T, n); }
 
 }  // namespace lsc

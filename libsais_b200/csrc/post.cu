@@ -429,4 +429,147 @@ void run_narrow(Ctx &c, const i64 *src, u32 *dst, u64 n)
     if (n) LSC_LAUNCH(c, KC_CONVERT, (double)n * 12, narrow_kernel, (u32)ceil_div(n, 256), 256, 0, src, dst, n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16-bit symbols (reference src/libsais16.c, include/libsais16.h).  The SA / PLCP cores run on the text widened to 32-bit
+// symbols (the integer-alphabet path); this section holds what is specific to uint16_t texts: the 65536-bin frequency
+// table, BWT rows gathered from the suffix array, and the inverse BWT over a 65536-symbol alphabet (psi by TWO stable
+// onesweep passes of (symbol, row); F[x] is read from the sorted symbols instead of a cumulative table).
+// ---------------------------------------------------------------------------------------------
+typedef uint16_t u16;
+
+__global__ void __launch_bounds__(256) widen16_kernel(const u16 *__restrict__ src, u32 *__restrict__ dst, u64 n)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = (u32)src[i];
+}
+void run_widen16(Ctx &c, const u16 *src, u32 *dst, u64 n)
+{
+    if (n) LSC_LAUNCH(c, KC_CONVERT, (double)n * 6, widen16_kernel, (u32)ceil_div(n, 256), 256, 0, src, dst, n);
+}
+
+__global__ void __launch_bounds__(256) hist_u16_kernel(const u16 *__restrict__ T, u64 n, unsigned long long *__restrict__ hist)
+{
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) atomicAdd(&hist[T[i]], 1ull);
+}
+void run_hist_u16(Ctx &c, const u16 *d_T, u64 n, u64 *d_hist)
+{
+    c.check(cudaMemsetAsync(d_hist, 0, 65536 * sizeof(u64), c.stream));
+    if (!n) return;
+    const u64 want = ceil_div(n, 256 * 8);
+    const u32 grid = (u32)(want < (u64)c.sm_count * 16 ? want : (u64)c.sm_count * 16);
+    LSC_LAUNCH(c, KC_HIST_SYM, (double)n * 2, hist_u16_kernel, grid, 256, 0, d_T, n, (unsigned long long *)d_hist);
+}
+
+// slot of suffix 0 (+1) and the aux samples I[p / r] = slot + 1 for p % r == 0, from a finished suffix array
+__global__ void __launch_bounds__(256)
+sa_primary_aux_kernel(const u32 *__restrict__ SA, u64 n, u64 aux_mask, int aux_shift, u32 *__restrict__ aux_I, u64 *__restrict__ primary)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const u32 p = SA[i];
+    if (p == 0) *primary = i + 1;
+    if (aux_I != nullptr && ((u64)p & aux_mask) == 0) aux_I[p >> aux_shift] = (u32)i + 1;
+}
+// U[0] = T[n-1]; slot i (suffix p != 0) -> U[i + (i < p0)] = T[p - 1]   (reference assembly src/libsais16.c, same rule as :7110-7118 of libsais.c)
+__global__ void __launch_bounds__(256)
+bwt16_gather_kernel(const u16 *__restrict__ T, const u32 *__restrict__ SA, u16 *__restrict__ U, u64 n, u64 p0)
+{
+    u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0) U[0] = T[n - 1];
+    const u32 p = SA[i];
+    if (p != 0) U[i + (i < p0 ? 1 : 0)] = T[p - 1];
+}
+// returns the primary index (>= 1) in *primary_out; d_U must not alias d_T
+int run_bwt16(Ctx &c, const u16 *d_T, const u32 *d_SA, u16 *d_U, u64 n, u64 aux_r, u32 *d_I, u64 *primary_out)
+{
+    u64 *dp = c.d_scalars + S_PRIMARY;
+    c.check(cudaMemsetAsync(dp, 0, sizeof(u64), c.stream));
+    LSC_LAUNCH(c, KC_BWT, (double)n * 4, sa_primary_aux_kernel, (u32)ceil_div(n, 256), 256, 0, d_SA, n,
+               aux_r ? aux_r - 1 : ~0ull, aux_r ? bits_for(aux_r) - 1 : 0, aux_r ? d_I : (u32 *)nullptr, dp);
+    c.check(cudaMemcpyAsync(c.h_scalars + S_PRIMARY, dp, sizeof(u64), cudaMemcpyDeviceToHost, c.stream));
+    if (!c.sync()) return -2;
+    const u64 primary = c.h_scalars[S_PRIMARY];
+    if (primary < 1 || primary > n) return -2;
+    LSC_LAUNCH(c, KC_BWT, (double)n * 8, bwt16_gather_kernel, (u32)ceil_div(n, 256), 256, 0, d_T, d_SA, d_U, n, primary - 1);
+    *primary_out = primary;
+    return c.failed() ? -2 : 0;
+}
+
+// inverse BWT walks with F read from the sorted symbols: F[x] = sorted[x - 1] for rows x >= 1
+__global__ void __launch_bounds__(128)
+unbwt16_walk2_kernel(const u32 *__restrict__ psi, const u16 *__restrict__ sorted, u64 n, u64 primary, int logS, u64 nsplit,
+                     const u64 *__restrict__ dist, u16 *__restrict__ U)
+{
+    u64 id = (u64)blockIdx.x * 128 + threadIdx.x;
+    if (id >= nsplit) return;
+    const u64 smask = ((u64)1 << logS) - 1;
+    u64 x = id ? (id << logS) : primary;
+    u64 d = dist[id];
+    if (d > n) return;
+    u64 t = n - d, steps = 0;
+    do {
+        if (t < n && x >= 1) U[t] = sorted[x - 1];
+        ++t; ++steps;
+        x = psi[x];
+    } while (!unbwt_stop(x, smask, primary) && steps <= n);
+}
+__global__ void __launch_bounds__(128)
+unbwt16_walk_aux_kernel(const u32 *__restrict__ psi, const u16 *__restrict__ sorted, u64 n, u64 r, const u32 *__restrict__ I, u64 nchains, u16 *__restrict__ U)
+{
+    const u64 j = (u64)blockIdx.x * 128 + threadIdx.x;
+    if (j >= nchains) return;
+    u64 x = I[j];
+    const u64 t0 = j * r, t1 = t0 + r < n ? t0 + r : n;
+    for (u64 t = t0; t < t1; ++t) {
+        if (x > n || x < 1) return;                      // inconsistent samples
+        U[t] = sorted[x - 1];
+        x = psi[x];
+    }
+}
+
+size_t unbwt16_workspace_bytes(u64 n)
+{
+    u64 ns = (n >> unbwt_log_s(n)) + 2;
+    return (size_t)n * (4 + 4 + 2 + 2) + 64 + RadixSort<u16, u32>::temp_bytes(n) + ns * (4 + 4 + 4 + 8 + 8) + 16 * 256;
+}
+
+// d_B is CLOBBERED (it ends up holding the sorted symbols); d_U must not alias it
+int run_unbwt16(Ctx &c, u16 *d_B, u16 *d_U, u64 n, u64 primary, u64 aux_r, const u32 *d_I, u64 n_aux)
+{
+    const int logS = unbwt_log_s(n);
+    const u64 nsplit = (n >> logS) + 1;
+    u32 *pa = c.alloc_n<u32>(n + 1), *pb = c.alloc_n<u32>(n + 1);
+    u16 *kb = c.alloc_n<u16>(n);
+    void *temp = c.alloc(RadixSort<u16, u32>::temp_bytes(n));
+    u32 *nxt0 = c.alloc_n<u32>(nsplit), *nxt1 = c.alloc_n<u32>(nsplit), *len = c.alloc_n<u32>(nsplit);
+    u64 *dist0 = c.alloc_n<u64>(nsplit), *dist1 = c.alloc_n<u64>(nsplit);
+    if (!pa || !pb || !kb || !temp || !dist1) return -2;
+    u32 *err = (u32 *)(c.d_scalars + S_ERR);
+    c.check(cudaMemsetAsync(c.d_scalars + S_ERR, 0, sizeof(u64), c.stream));
+    c.check(cudaMemsetAsync(pa, 0, sizeof(u32), c.stream));
+    c.check(cudaMemsetAsync(pb, 0, sizeof(u32), c.stream));
+    LSC_LAUNCH(c, KC_UNBWT_PREP, (double)n * 4, unbwt_rows_kernel, (u32)ceil_div(n, 256), 256, 0, pa + 1, n, primary);
+    // two stable 8-bit passes of (symbol, row): psi[1..n] = rows in symbol order, the keys end up sorted (= F[1..n])
+    const int where = RadixSort<u16, u32>::sort(c, d_B, pa + 1, kb, pb + 1, n, 0, 16, temp, err);
+    if (where < 0) return -2;
+    const u32 *psi = where ? pb : pa;
+    const u16 *sorted = where ? kb : d_B;
+    if (d_I != nullptr && aux_r >= 2 && n_aux >= 2 && (aux_r <= 512 || n_aux >= 200000 || n < ((u64)1 << 20))) {
+        LSC_LAUNCH(c, KC_UNBWT_WALK, (double)n * 8, unbwt16_walk_aux_kernel, (u32)ceil_div(n_aux, 128), 128, 0, psi, sorted, n, aux_r, d_I, n_aux, d_U);
+        return c.failed() ? -2 : 0;
+    }
+    LSC_LAUNCH(c, KC_UNBWT_WALK, (double)n * 4, unbwt_walk1_kernel, (u32)ceil_div(nsplit, 128), 128, 0, psi, n, primary, logS, nsplit, nxt0, len);
+    LSC_LAUNCH(c, KC_UNBWT_RANK, (double)nsplit * 12, unbwt_dist_init_kernel, (u32)ceil_div(nsplit, 256), 256, 0, len, dist0, nsplit);
+    const int rounds = bits_for(nsplit) + 1;
+    u32 *ni = nxt0, *no = nxt1; u64 *di = dist0, *dout = dist1;
+    for (int r = 0; r < rounds; ++r) {
+        LSC_LAUNCH(c, KC_UNBWT_RANK, (double)nsplit * 24, unbwt_jump_kernel, (u32)ceil_div(nsplit, 256), 256, 0, ni, di, no, dout, nsplit);
+        u32 *tn = ni; ni = no; no = tn;
+        u64 *td = di; di = dout; dout = td;
+    }
+    LSC_LAUNCH(c, KC_UNBWT_WALK, (double)n * 8, unbwt16_walk2_kernel, (u32)ceil_div(nsplit, 128), 128, 0, psi, sorted, n, primary, logS, nsplit, di, d_U);
+    return c.failed() ? -2 : 0;
+}
+
 }  // namespace lsc
