@@ -79,6 +79,8 @@ struct PartArgs {
     u32 *err; int use_bulk;
     void *const *kptr;      // non-null: per-digit output bases (device array of 256 pointers each), possibly in PEER memory:
     void *const *vptr;      //   element i of digit d goes to kptr[d][i] / vptr[d][i] -- the fused route + exchange of dist64.cu
+    int out32 = 0;          // part_pipe_kernel only: write the low 32 bits of the 64-bit keys (second MSD level when the key bits
+                            // below the 16-bit bucket prefix fit a word: the bucket is implied by where the element lands)
 };
 
 template <typename KeyT, typename ValT, int THREADS, int IPT, int MINB, typename ST, typename Src, bool SEG>
@@ -570,7 +572,7 @@ part_pipe_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *
                 if (full || idx < count) {
                     const u64 k = skeys[idx];
                     const u64 g = sm.goff[digit_of(k, shift, dmask)] + idx;
-                    kout[g] = k;
+                    if (a.out32) reinterpret_cast<u32 *>(kout)[g] = (u32)k; else kout[g] = k;
                     vout[g] = sm.vals[idx];
                 }
             }
@@ -944,10 +946,69 @@ __device__ __forceinline__ void bucket_bin_range(const BucketSmem &sm, u32 bin, 
     beg = bin == 0 ? 0u : ((bin & 1) ? (wv & 0xFFFFu) : (sm.bins[(bin >> 1) - 1] >> 16));
 }
 
+// Fused rank stage (round 0): equal k-mers always share a bin, so the counting loop that ranks an element inside its
+// bin also tells whether it heads its group (no equal k-mer sorts before it) and whether the group has other members.
+// With `on` the kernel writes, instead of the sorted key array that rank_flags_kernel<true> would read back:
+// positions in slot order (= the suffix array of round 0), the BWT row bytes, the head / active bits in the rank
+// stage's mask layout (one byte per 4 slots: heads | actives << 4; rank_agg_kernel derives the per-warp and per-tile
+// aggregates from them), and the primary index / aux samples of the suffixes that are already final.
+// Suffixes that run past the end of the text (position >= tail_start) are groups of their own (sa_core.cu, end-of-text rule).
+struct BucketFuse {
+    int on;
+    u32 *masks; u8 *rows; u64 tail_start;
+    u64 aux_mask; int aux_shift; u32 *aux_I; u64 *primary;
+};
+
+// flag bytes of the tile (bit 0 head, bit 1 active) in slot order -> mask bytes; slots [s, s + cnt) of the array
+__device__ __forceinline__ void bucket_emit_masks(const u8 *sflag, u64 s, u32 cnt, u32 *masks, int tid)
+{
+    const u64 w0 = s >> 4, w1 = (s + cnt - 1) >> 4;                 // mask words: 16 slots each
+    for (u64 w = w0 + tid; w <= w1; w += kBucketThreads) {
+        u32 word = 0;
+        const u64 g0 = w << 4;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const u64 g = g0 + q;
+            if (g >= s && g < s + cnt) {
+                const u32 f = sflag[(u32)(g - s)];
+                word |= ((f & 1u) << (q & 3) | ((f >> 1) & 1u) << (4 + (q & 3))) << (8 * (q >> 2));
+            }
+        }
+        if (g0 >= s && g0 + 16 <= s + cnt) masks[w] = word;
+        else if (word) atomicOr(&masks[w], word);                    // words shared with a neighbouring tile (masks are zeroed)
+    }
+}
+__device__ __forceinline__ void bucket_emit_rows(const u8 *srow, u64 s, u32 cnt, u8 *rows, int tid)
+{
+    // bytes up to the first 4-byte boundary, aligned words, the rest
+    u32 lead = (u32)((4 - ((uintptr_t)(rows + s) & 3)) & 3);
+    if (lead > cnt) lead = cnt;
+    const u32 nwords = (cnt - lead) >> 2, tail0 = lead + nwords * 4;
+    if ((u32)tid < lead) rows[s + tid] = srow[tid];
+    u32 *dst = reinterpret_cast<u32 *>(rows + s + lead);
+    for (u32 w = tid; w < nwords; w += kBucketThreads) {
+        const u8 *b = srow + lead + 4 * w;
+        dst[w] = (u32)b[0] | (u32)b[1] << 8 | (u32)b[2] << 16 | (u32)b[3] << 24;
+    }
+    if ((u32)tid < cnt - tail0) rows[s + tail0 + tid] = srow[tail0 + tid];
+}
+
+// key of element idx of the partitioned array.  in32: the array holds only the key bits below the 16-bit bucket
+// prefix (PartArgs::out32); the prefix is the bucket the element lies in, B0 <= B < B0 + nb with boff[B] <= idx < boff[B+1].
+__device__ __forceinline__ u64 bucket_load_key(const u64 *__restrict__ kin, int in32, u64 idx, const u32 *__restrict__ boff, u32 B0, u32 nb, int lowbits)
+{
+    if (!in32) return kin[idx];
+    const u32 k32 = reinterpret_cast<const u32 *>(kin)[idx];
+    u32 lo = B0, hi = B0 + nb;
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if ((u64)boff[mid] <= idx) lo = mid; else hi = mid; }
+    return ((u64)lo << lowbits) | (u64)k32;
+}
+
 static __global__ void __launch_bounds__(kBucketThreads, 2)
 bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, const uint4 *__restrict__ tb,
                    u64 n, u32 C, int key_shift, int R,             // R = K - 16: k-mer bits below the bucket prefix
-                   u64 *__restrict__ kout, u32 *__restrict__ vout, u32 *err)
+                   u64 *__restrict__ kout, u32 *__restrict__ vout, u32 *err, const BucketFuse fz,
+                   const u32 *__restrict__ boff, const int in32)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BucketSmem &sm = *reinterpret_cast<BucketSmem *>(smem_raw);
@@ -976,7 +1037,7 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
             const u32 i = q * kBucketThreads + tid;
             keep[q] = 0;
             if (i < cnt) {
-                const u64 key = kin[s + i];
+                const u64 key = bucket_load_key(kin, in32, s + i, boff, B0, nb, R + key_shift);
                 const u32 p = vin[s + i];
                 const u64 comp = (((key >> key_shift) - kbase) << 32) | (u64)(~p);
                 keep[q] = comp;
@@ -986,7 +1047,7 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
             }
         }
         for (u32 i = kBucketKeep * kBucketThreads + tid; i < cnt; i += kBucketThreads) {
-            const u64 rel = (kin[s + i] >> key_shift) - kbase;
+            const u64 rel = (bucket_load_key(kin, in32, s + i, boff, B0, nb, R + key_shift) >> key_shift) - kbase;
             const u32 bin = min((u32)(rel >> sh), (u32)kBucketBins - 1);
             atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
         }
@@ -1007,7 +1068,7 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
             }
         }
         for (u32 i = kBucketKeep * kBucketThreads + tid; i < cnt; i += kBucketThreads) {
-            const u64 key = kin[s + i];
+            const u64 key = bucket_load_key(kin, in32, s + i, boff, B0, nb, R + key_shift);
             const u32 p = vin[s + i];
             const u64 comp = (((key >> key_shift) - kbase) << 32) | (u64)(~p);
             const u32 bin = min((u32)(comp >> csh), (u32)kBucketBins - 1);
@@ -1018,30 +1079,64 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
         }
         __syncthreads();
         // 4. rank inside the bin (composite words are distinct: the positions are), write to the final slot
+        if (!fz.on) {
+            for (u32 i = tid; i < cnt; i += kBucketThreads) {
+                const u64 comp = sm.keys[i];
+                const u32 bin = min((u32)(comp >> csh), (u32)kBucketBins - 1);
+                u32 beg, end;
+                bucket_bin_range(sm, bin, beg, end);
+                u32 r = 0;
+                for (u32 q = beg; q < end; ++q) r += sm.keys[q] < comp ? 1u : 0u;
+                const u64 o = s + beg + r;
+                kout[o] = (((comp >> 32) + kbase) << key_shift) | (u64)prevb[i];
+                vout[o] = ~(u32)comp;
+            }
+            return;
+        }
+        // fused rank stage: flag and row bytes staged in slot order behind prevb[] (the compact path leaves 3/4 of pos[] unused)
+        u8 *sflag = prevb + kBucketCap, *srow = prevb + 2 * kBucketCap;
+        const u32 ts = fz.tail_start > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)fz.tail_start;
         for (u32 i = tid; i < cnt; i += kBucketThreads) {
             const u64 comp = sm.keys[i];
             const u32 bin = min((u32)(comp >> csh), (u32)kBucketBins - 1);
             u32 beg, end;
             bucket_bin_range(sm, bin, beg, end);
-            u32 r = 0;
-            for (u32 q = beg; q < end; ++q) r += sm.keys[q] < comp ? 1u : 0u;
-            const u64 o = s + beg + r;
-            kout[o] = (((comp >> 32) + kbase) << key_shift) | (u64)prevb[i];
-            vout[o] = ~(u32)comp;
+            const u32 p = ~(u32)comp, km = (u32)(comp >> 32);
+            const bool tail = p >= ts;
+            u32 r = 0, same = 0, before = 0;                             // members of my group (equal k-mer, not past the end), those before me
+            for (u32 q = beg; q < end; ++q) {
+                const u64 x = sm.keys[q];
+                const bool lt = x < comp;
+                const bool eq = (u32)(x >> 32) == km && ~(u32)x < ts;
+                r += lt ? 1u : 0u; same += eq ? 1u : 0u; before += (eq && lt) ? 1u : 0u;
+            }
+            const bool head = tail || before == 0, active = !tail && same > 1;
+            const u32 d = beg + r;
+            sflag[d] = (u8)((head ? 1u : 0u) | (active ? 2u : 0u));
+            srow[d] = prevb[i];
+            const u64 o = s + d;
+            vout[o] = p;
+            if (!active) {
+                if (p == 0) *fz.primary = o + 1;
+                if (fz.aux_I && ((u64)p & fz.aux_mask) == 0) fz.aux_I[p >> fz.aux_shift] = (u32)o + 1;
+            }
         }
+        __syncthreads();
+        bucket_emit_masks(sflag, s, cnt, fz.masks, tid);
+        if (fz.rows) bucket_emit_rows(srow, s, cnt, fz.rows, tid);
         return;
     }
 
     // ---- generic path: u64 key + u32 position per element
     for (u32 i = tid; i < cnt; i += kBucketThreads) {
-        const u64 km = kin[s + i] >> key_shift;
+        const u64 km = bucket_load_key(kin, in32, s + i, boff, B0, nb, R + key_shift) >> key_shift;
         const u32 bin = min((u32)((km - kbase) >> sh), (u32)kBucketBins - 1);
         atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
     }
     __syncthreads();
     bucket_scan_bins(sm, tid, lane, warp);
     for (u32 i = tid; i < cnt; i += kBucketThreads) {
-        const u64 key = kin[s + i];
+        const u64 key = bucket_load_key(kin, in32, s + i, boff, B0, nb, R + key_shift);
         const u32 p = vin[s + i];
         const u32 bin = min((u32)(((key >> key_shift) - kbase) >> sh), (u32)kBucketBins - 1);
         const u32 old = atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
@@ -1056,14 +1151,26 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
         const u32 bin = min((u32)((km - kbase) >> sh), (u32)kBucketBins - 1);
         u32 beg, end;
         bucket_bin_range(sm, bin, beg, end);
-        u32 r = 0;
+        u32 r = 0, same = 0, before = 0;
         for (u32 q = beg; q < end; ++q) {
             const u64 kj = sm.keys[q] >> key_shift;
-            r += (kj < km || (kj == km && sm.pos[q] > p)) ? 1u : 0u;
+            const bool lt = kj < km || (kj == km && sm.pos[q] > p);
+            const bool eq = kj == km && (u64)sm.pos[q] < fz.tail_start;
+            r += lt ? 1u : 0u; same += eq ? 1u : 0u; before += (eq && lt) ? 1u : 0u;
         }
         const u64 o = s + beg + r;
-        kout[o] = key;
         vout[o] = p;
+        if (!fz.on) { kout[o] = key; continue; }
+        // fused rank stage without staging (rare path: very small or oddly spread inputs): bits straight into the zeroed masks
+        const bool tail = (u64)p >= fz.tail_start;
+        const bool head = tail || before == 0, active = !tail && same > 1;
+        const u32 bits = ((head ? 1u : 0u) << (o & 3) | (active ? 1u : 0u) << (4 + (o & 3))) << (8 * ((o >> 2) & 3));
+        if (bits) atomicOr(&fz.masks[o >> 4], bits);
+        if (fz.rows) fz.rows[o] = (u8)(key & lowmask);
+        if (!active) {
+            if (p == 0) *fz.primary = o + 1;
+            if (fz.aux_I && ((u64)p & fz.aux_mask) == 0) fz.aux_I[p >> fz.aux_shift] = (u32)o + 1;
+        }
     }
 }
 

@@ -1,0 +1,337 @@
+// po_rounds.cuh -- rounds >= 1 of the prefix doubling on a POSITION-ORDERED active list: one fused kernel per round.
+//
+// After round 0 the unresolved suffixes lie in slot order, group after group, and neighbouring groups have nothing
+// to do with each other in the text: a tile's look-ups ISA[p + h] and its rank updates ISA[p] touch as many DRAM
+// granules as it has elements (ncu, round 1: 118 bytes fetched per 4-byte look-up).  But a doubling round never
+// moves anything between groups, so the ORDER OF THE GROUPS in the active list is free.  Once, after round 0, the
+// groups are sorted by the text position of their head suffix (members keep their slot order).  In a repetitive
+// text the group of the copies of offset x is then followed by the group of the copies of x + 1: a tile of ~20
+// groups of ~100 copies reads and updates ~100 runs of ~20 consecutive ISA entries instead of 2000 scattered ones, and
+// tiles taken in list order walk those runs forward through L2.  The active record is (position, rank of the
+// group) -- a group occupies the slots [rank, rank + size), so slots and group boundaries need no arrays of
+// their own.
+//
+// po_round_kernel, one tile = the groups that start in a window of the list (whole groups, <= kPoCap elements):
+//   gather  r = ISA[p + h] + 1
+//   order   every element counts the members of its group that precede it (key (r, index): unique); a thread owns
+//           8 consecutive elements and shares each shared-memory load between them
+//   rank    new sub-group heads by neighbour compare in sorted order; new rank = old rank + offset of the head
+//   emit    final suffixes (sub-group of one): SA[slot], BWT row, primary index, aux sample -- each written once,
+//           when it is known; changed ranks as (position, rank) pairs at the element's list index (applied to ISA
+//           by po_apply_kernel AFTER the round: a round must read the ranks of the round before); the suffixes
+//           that stay active, compacted in list order through a chained scan over the tiles (atomic tickets,
+//           decoupled look-back on one status word per tile)
+// Replaces local_count / local_sort + rank_flags + rank_scan + rank_apply + the partition pass and scatter of the
+// ISA update: ~50 instead of ~300 bytes of traffic per active suffix and round.
+// (Reference counterpart: none -- libsais is SA-IS, src/libsais.c:2157-4101; this is the B200-native SA core.)
+#pragma once
+#include "radix_sort.cuh"
+
+namespace lsc {
+
+static const int kPoCap = 2048;                  // elements a tile can hold
+static const int kPoThreads = 256;
+static const int kPoIPT = kPoCap / kPoThreads;   // 8
+static const int kPoWarps = kPoThreads / 32;
+static const u32 kPoNone = 0xFFFFFFFFu;          // pair slot without an update
+static const u32 kPoMaxGroup = 1024;             // larger groups after round 0: the slot-ordered path of round 1 handles the text
+
+struct PoArgs {
+    const u64 *kv_keys; const u32 *kv_vals;      // first round: rank = low word of kv_keys[j], position = kv_vals[j] (output of the group sort)
+    const u32 *a_pos, *a_rank;                   // later rounds
+    u64 N, n, h; u32 C;                          // list length, text length, sorted prefix length, window of a tile
+    const u32 *ISA;
+    u32 *o_pos, *o_rank;                         // suffixes that stay active
+    u32 *pair_pos, *pair_rank;                   // [N] rank updates (kPoNone: none)
+    u32 *SA; u8 *rows; const u8 *text; u64 aux_mask; int aux_shift; u32 *aux_I; u64 *primary;
+    u64 *status; u32 *ticket; u64 *out_counts;   // chained scan; out_counts[0] = active suffixes, [1] = active groups after the round
+    u32 *err;
+};
+
+template <bool KV> __device__ __forceinline__ u32 po_rank_at(const PoArgs &a, u64 j)
+{
+    return KV ? reinterpret_cast<const u32 *>(a.kv_keys)[2 * j] : a.a_rank[j];
+}
+template <bool KV> __device__ __forceinline__ u32 po_pos_at(const PoArgs &a, u64 j) { return KV ? a.kv_vals[j] : a.a_pos[j]; }
+
+// exclusive max-scan and sum-scan over the threads of the CTA (two barriers)
+__device__ __forceinline__ void po_block_scan(u32 mymax, u32 mysum, u32 &exmax, u32 &exsum, u32 &total, u32 (*s_scan)[kPoWarps], int lane, int warp)
+{
+    u32 m = mymax, s = mysum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 om = __shfl_up_sync(0xffffffffu, m, off), os = __shfl_up_sync(0xffffffffu, s, off);
+        if (lane >= off) { m = om > m ? om : m; s += os; }
+    }
+    if (lane == 31) { s_scan[0][warp] = m; s_scan[1][warp] = s; }
+    u32 em = __shfl_up_sync(0xffffffffu, m, 1), es = __shfl_up_sync(0xffffffffu, s, 1);
+    if (lane == 0) { em = 0; es = 0; }
+    __syncthreads();
+    u32 cm = 0, cs = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kPoWarps; ++w) {
+        const u32 x = s_scan[0][w], y = s_scan[1][w];
+        if (w < warp) { cm = x > cm ? x : cm; cs += y; }
+        tot += y;
+    }
+    exmax = em > cm ? em : cm; exsum = es + cs; total = tot;
+    __syncthreads();
+}
+
+template <bool KV>
+__global__ void __launch_bounds__(kPoThreads, 4)
+po_round_kernel(const PoArgs a)
+{
+    __shared__ __align__(16) u64 comp[kPoCap];   // gathered rank, then (group start << 43 | rank << 11 | index); after the counting: sorted ranks, then new ranks (u32 view)
+    __shared__ __align__(16) u32 s_p[kPoCap];    // positions: list order, then sorted order
+    __shared__ __align__(16) u32 s_rk[kPoCap];   // rank of the element's group (the same for every index of a group)
+    __shared__ __align__(16) unsigned short s_gs[kPoCap];   // index of the first element of the group
+    __shared__ __align__(16) unsigned short s_ge[kPoCap];   // at a group's first index: one past its last; after the ranking: output offset | flags
+    __shared__ u32 s_scan[2][kPoWarps];
+    __shared__ u32 bounds[2];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 *s_r2 = reinterpret_cast<u32 *>(comp);
+
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    if (tid < 2) bounds[tid] = 0xFFFFFFFFu;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 N = a.N, t0 = (u64)tile * a.C;
+
+    // ---- the tile: from the first group head at or after t0 to the first at or after t0 + C
+    bool ok = true;
+    for (int which = 0; which < 2; ++which) {
+        const u64 target = t0 + (u64)which * a.C;
+        if (target >= N) { if (tid == 0) bounds[which] = (u32)(N - t0); continue; }
+        bool found = false;
+        for (u32 off = 0; !found; off += kPoThreads) {
+            const u64 j = target + off + tid;
+            const bool hd = j < N ? (j == 0 || po_rank_at<KV>(a, j) != po_rank_at<KV>(a, j - 1)) : j == N;
+            if (hd) atomicMin(&bounds[which], (u32)(j - t0));
+            found = __syncthreads_or(hd) != 0;
+            if (!found && off > (u32)kPoCap) { ok = false; found = true; }
+        }
+    }
+    __syncthreads();
+    ok = ok && bounds[1] >= bounds[0] && bounds[1] - bounds[0] <= (u32)kPoCap;
+    if (!ok && tid == 0) *a.err = 2;             // a group larger than promised
+    const u32 cnt = ok ? bounds[1] - bounds[0] : 0;
+    const u64 s = t0 + (ok ? bounds[0] : 0);
+
+    u32 total = 0, act_groups = 0;
+    u32 e_excl[kPoIPT];                          // phase "emit" state of my 8 sorted elements
+    if (cnt) {                                   // uniform over the CTA
+        // ---- gather (strided: coalesced list loads, 8 look-ups in flight per thread)
+        {
+            u32 p[kPoIPT], rk[kPoIPT], r[kPoIPT];
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                const u32 idx = i * kPoThreads + tid;
+                p[i] = idx < cnt ? po_pos_at<KV>(a, s + idx) : 0;
+                rk[i] = idx < cnt ? po_rank_at<KV>(a, s + idx) : 0;
+            }
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                const u32 idx = i * kPoThreads + tid;
+                const u64 q = (u64)p[i] + a.h;
+                r[i] = (idx < cnt && q < a.n) ? a.ISA[q] + 1 : 0;
+            }
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                const u32 idx = i * kPoThreads + tid;
+                if (idx < cnt) { s_p[idx] = p[i]; s_rk[idx] = rk[i]; comp[idx] = (u64)r[i]; }
+            }
+        }
+        __syncthreads();
+        const u32 idx0 = (u32)tid * kPoIPT;
+        const int nv = idx0 < cnt ? (cnt - idx0 < (u32)kPoIPT ? (int)(cnt - idx0) : kPoIPT) : 0;
+        // ---- group starts (blocked: a thread owns 8 consecutive elements)
+        {
+            u32 rk[kPoIPT];
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) rk[i] = i < nv ? s_rk[idx0 + i] : 0;
+            const u32 rprev = (nv && idx0 > 0) ? s_rk[idx0 - 1] : 0;
+            u32 hm = 0, last = 0;
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                const bool hd = i < nv && (idx0 + i == 0 || rk[i] != (i ? rk[i - 1] : rprev));
+                if (hd) { hm |= 1u << i; last = idx0 + i; }
+            }
+            u32 carry, dummy, dummy2;
+            po_block_scan(last, 0, carry, dummy, dummy2, s_scan, lane, warp);
+            u32 cur = carry;
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                if (i < nv) {
+                    const u32 idx = idx0 + i;
+                    if ((hm >> i) & 1u) { if (idx > 0) s_ge[cur] = (unsigned short)idx; cur = idx; }
+                    s_gs[idx] = (unsigned short)cur;
+                    if (idx == cnt - 1) s_ge[cur] = (unsigned short)cnt;
+                    comp[idx] = ((u64)cur << 43) | ((comp[idx] & 0xFFFFFFFFull) << 11) | (u64)idx;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- order: sorted index = elements of the tile with a smaller (group, rank, index) key.  Everything before
+        // the group of my first element is smaller, everything after the group of my last one is larger.
+        u32 d[kPoIPT], pp[kPoIPT], rr[kPoIPT];
+        {
+            u64 c[kPoIPT];
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) { c[i] = i < nv ? comp[idx0 + i] : 0; d[i] = 0; pp[i] = i < nv ? s_p[idx0 + i] : 0; }
+            if (nv) {
+                const u32 lo = (u32)(c[0] >> 43);
+                const u32 hi = s_ge[(u32)(comp[idx0 + nv - 1] >> 43)];
+#pragma unroll 2
+                for (u32 j = lo; j < hi; ++j) {
+                    const u64 x = comp[j];
+#pragma unroll
+                    for (int i = 0; i < kPoIPT; ++i) d[i] += (u32)(x < c[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < kPoIPT; ++i) d[i] += lo;
+            }
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) rr[i] = (u32)(c[i] >> 11);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kPoIPT; ++i) if (i < nv) { s_p[d[i]] = pp[i]; s_r2[d[i]] = rr[i]; }
+        __syncthreads();
+        // ---- rank (blocked over the sorted order): sub-group heads, finals, new ranks, output offsets
+        {
+            u32 r2[kPoIPT + 1]; u32 gs[kPoIPT + 1];
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) { r2[i] = i < nv ? s_r2[idx0 + i] : 0; gs[i] = i < nv ? s_gs[idx0 + i] : 0; }
+            const bool more = nv == kPoIPT && idx0 + kPoIPT < cnt;
+            r2[kPoIPT] = more ? s_r2[idx0 + kPoIPT] : 0; gs[kPoIPT] = more ? s_gs[idx0 + kPoIPT] : 0;
+            const u32 r2prev = (nv && idx0 > 0) ? s_r2[idx0 - 1] : 0;
+            u32 nhm = 0, actm = 0, last = 0;
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                if (i < nv) {
+                    const u32 dd = idx0 + i;
+                    const bool nh = dd == gs[i] || r2[i] != (i ? r2[i - 1] : r2prev);
+                    const bool last_of_tile = dd + 1 >= cnt;
+                    const bool nn = last_of_tile || gs[i + 1] == dd + 1 || r2[i + 1] != r2[i];
+                    if (nh) { nhm |= 1u << i; last = dd; }
+                    if (!(nh && nn)) actm |= 1u << i;
+                }
+            }
+            u32 carry, excl;
+            po_block_scan(last, (u32)__popc(actm), carry, excl, total, s_scan, lane, warp);
+            u32 cur = carry;
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                e_excl[i] = 0;
+                if (i < nv) {
+                    const u32 dd = idx0 + i;
+                    if ((nhm >> i) & 1u) cur = dd;
+                    const bool act = (actm >> i) & 1u;
+                    const u32 newrank = s_rk[dd] + (cur - gs[i]);
+                    act_groups += (u32)(act && ((nhm >> i) & 1u));
+                    // offset among the tile's actives (< 2048: 11 bits) | active << 14 | rank changed << 15
+                    s_ge[dd] = (unsigned short)((excl + (u32)__popc(actm & ((1u << i) - 1u))) | (act ? 1u << 14 : 0u) | (cur != gs[i] ? 1u << 15 : 0u));
+                    s_r2[dd] = newrank;
+                }
+            }
+        }
+    }
+    // ---- chained scan over the tiles: where this tile's active suffixes go
+    act_groups = __reduce_add_sync(0xffffffffu, act_groups);
+    if (lane == 0 && act_groups) atomicAdd((unsigned long long *)(a.out_counts + 1), (unsigned long long)act_groups);
+    if (warp == 0) {
+        typedef StWord<u64> W;
+        if (lane == 0) st_relaxed(a.status + tile, tile == 0 ? W::inc(total) : W::agg(total));
+        u64 excl = 0;
+        if (tile > 0) {
+            i64 look = (i64)tile - 1;
+            u32 spins = 0;
+            for (;;) {
+                const i64 idx = look - lane;
+                const u64 w = idx >= 0 ? ld_relaxed(a.status + idx) : W::inc(0);
+                const u32 f = W::flag(w);
+                const u32 incm = __ballot_sync(0xffffffffu, f == 2);
+                const int first = incm ? __ffs(incm) - 1 : 31;                 // nearest tile with an inclusive prefix
+                const u32 need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+                if (__ballot_sync(0xffffffffu, f == 0) & need) {                // someone on the way has not published yet
+                    if (++spins > kSpinLimit) { if (lane == 0) *a.err = 1; break; }
+                    continue;
+                }
+                u64 v = lane <= first ? W::val(w) : 0;
+#pragma unroll
+                for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                excl += v;
+                if (incm) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed(a.status + tile, W::inc(excl + total));
+        }
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == gridDim.x - 1) a.out_counts[0] = excl + total;
+        }
+    }
+    __syncthreads();
+    if (!cnt) return;
+    // ---- emit (strided over the sorted order)
+    const u64 base = s_base;
+#pragma unroll
+    for (int i = 0; i < kPoIPT; ++i) {
+        const u32 dd = i * kPoThreads + tid;
+        if (dd < cnt) {
+            const u32 p = s_p[dd], meta = s_ge[dd], newrank = s_r2[dd];
+            const bool act = (meta >> 14) & 1u, changed = (meta >> 15) & 1u;
+            a.pair_pos[s + dd] = changed ? p : kPoNone;
+            a.pair_rank[s + dd] = newrank;
+            if (act) {
+                const u64 o = base + (meta & 0x3FFFu);
+                a.o_pos[o] = p; a.o_rank[o] = newrank;
+            } else {
+                // final: a sub-group of one; its rank is its slot
+                if (a.SA) a.SA[newrank] = p;
+                if (p == 0) *a.primary = (u64)newrank + 1;
+                else if (a.rows) a.rows[newrank] = a.text[p - 1];
+                if (a.aux_I && ((u64)p & a.aux_mask) == 0) a.aux_I[p >> a.aux_shift] = newrank + 1;
+            }
+        }
+    }
+}
+
+// ISA[p] = rank for the pairs of the round (after the round kernel: the round reads the previous ranks)
+static __global__ void __launch_bounds__(256)
+po_apply_kernel(const u32 *__restrict__ pair_pos, const u32 *__restrict__ pair_rank, u64 N, u32 *__restrict__ ISA)
+{
+    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    const u32 p = ld_stream(pair_pos + j);
+    if (p != kPoNone) ISA[p] = ld_stream(pair_rank + j);
+}
+
+// ---- the one-time reordering of the groups by the text position of their head suffix
+// table of the group heads: position and slot (dense group ids from the rank stage of round 0)
+static __global__ void __launch_bounds__(256)
+po_heads_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp, const u32 *__restrict__ a_slot, u64 N,
+                u32 *__restrict__ head_pos, u32 *__restrict__ head_slot)
+{
+    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    const u32 g = a_grp[j];
+    if (j == 0 || a_grp[j - 1] != g) { head_pos[g] = a_pos[j]; head_slot[g] = a_slot[j]; }
+}
+
+// sort key (head position << 32 | head slot = rank of the group), value = position
+static __global__ void __launch_bounds__(256)
+po_keys_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp, const u32 *__restrict__ head_pos,
+               const u32 *__restrict__ head_slot, u64 N, u64 *__restrict__ keys, u32 *__restrict__ vals)
+{
+    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    const u32 g = a_grp[j];
+    keys[j] = ((u64)head_pos[g] << 32) | (u64)head_slot[g];
+    vals[j] = a_pos[j];
+}
+
+}  // namespace lsc

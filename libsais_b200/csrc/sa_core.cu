@@ -29,6 +29,7 @@
 #include "scatter.cuh"
 #include "local_sort.cuh"
 #include "partition.cuh"
+#include "po_rounds.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -371,6 +372,34 @@ rank_flags_kernel(const RankArgs a)
     }
 }
 
+// Aggregates of rank_flags from the mask bytes alone (round 0 of the MSD path: bucket_sort_kernel wrote the masks,
+// partition.cuh BucketFuse): per warp and per tile the slot of the last head, the active suffixes, the active groups.
+__global__ void __launch_bounds__(kRankThreads)
+rank_agg_kernel(const u32 *__restrict__ masks, u64 N, u32 *__restrict__ wagg, u32 *__restrict__ tagg, u64 ntiles)
+{
+    __shared__ u32 s_wagg[3][kRankWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 tile = blockIdx.x;
+    const u64 j0 = tile * kRankTile + (u64)tid * 4;
+    const u32 mb = j0 < N ? reinterpret_cast<const u8 *>(masks)[j0 >> 2] : 0u;
+    const u32 h = mb & 15u, am = mb >> 4, gm = am & h;
+    const u32 w_head = __reduce_max_sync(0xffffffffu, h ? (u32)j0 + (u32)(31 - __clz(h)) : 0u);
+    const u32 w_act = __reduce_add_sync(0xffffffffu, (u32)__popc(am));
+    const u32 w_grp = __reduce_add_sync(0xffffffffu, (u32)__popc(gm));
+    if (lane == 0) {
+        u32 *wa = wagg + (tile * kRankWarps + warp) * 3;
+        wa[0] = w_head; wa[1] = w_act; wa[2] = w_grp;
+        s_wagg[0][warp] = w_head; s_wagg[1][warp] = w_act; s_wagg[2][warp] = w_grp;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        u32 r = 0;
+#pragma unroll
+        for (int w = 0; w < kRankWarps; ++w) { u32 v = s_wagg[tid][w]; r = tid == 0 ? (v > r ? v : r) : r + v; }
+        tagg[(u64)tid * ntiles + tile] = r;
+    }
+}
+
 // Three CTAs (one per aggregate): exclusive scan of the tile aggregates in place (SoA:
 // tagg[q * ntiles + tile]); totals -> out_counts[0..1].  Each warp owns a contiguous segment of
 // tiles and walks it 32 tiles at a time (coalesced loads, shuffle scan, running carry): reduce,
@@ -518,7 +547,9 @@ rank_apply_kernel(const RankArgs a)
     }
 }
 
-// Lazy ISA: rank of a round-0 singleton q, recomputed from the sorted round-0 keys.
+// Lazy ISA: rank of a round-0 singleton q, recomputed from the sorted round-0 keys (s0_keys == nullptr: from the
+// k-mers of the suffixes in slot order -- the fused MSD path never writes the sorted keys; later rounds only
+// permute positions inside groups of equal k-mers, so the suffix array in progress serves as s0_pos).
 struct LazyArgs { const u64 *words; int b; int K; const u64 *s0_keys; const u32 *s0_pos; int key_shift; u64 tail_start; u64 n; };
 
 __device__ __forceinline__ u32 lazy_rank(const LazyArgs &la, u64 q)
@@ -527,7 +558,8 @@ __device__ __forceinline__ u32 lazy_rank(const LazyArgs &la, u64 q)
     u64 lo = 0, hi = la.n;                               // lower bound of kq among the sorted k-mers
     while (lo < hi) {
         u64 mid = (lo + hi) >> 1;
-        if ((la.s0_keys[mid] >> la.key_shift) < kq) lo = mid + 1; else hi = mid;
+        const u64 km = la.s0_keys ? la.s0_keys[mid] >> la.key_shift : kmer_at(la.words, (u64)la.s0_pos[mid], la.b, la.K);
+        if (km < kq) lo = mid + 1; else hi = mid;
     }
     u64 s = lo;
     if (q >= la.tail_start) { while (s + 1 < la.n && (u64)la.s0_pos[s] != q) ++s; }       // its own slot
@@ -792,7 +824,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     // ---- MSD path (partition.cuh): when the 16-bit key prefixes spread the suffixes over small buckets (random
     // bytes, iid DNA: any near-uniform source), two UNSTABLE partition passes on the top 16 key bits and an
     // in-shared-memory finish of every bucket replace the K/8 stable LSD passes.  Same sorted arrays.
-    bool msd = false;
+    bool msd = false, msd_fused = false;
     u32 *m_boff = nullptr, *m_tstart = nullptr, *m_H = nullptr; u64 *m_base = nullptr; u64 m_maxb = 0, m_maxnt = 0;
     // LIBSAIS_CUDA_PART_PIPE: bit 0 = persistent double-buffered kernel for the first MSD level, bit 1 = for the second.
     // Measured on B200 (profiles/part_pass_r2.md): it pays for the array source (TMA prefetch: 2.15 -> 1.99 ms) and not for the
@@ -867,12 +899,23 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         pa.ticket = atomic_tickets ? tickets + 1 : nullptr;
         LSC_LAUNCH(c, KC_SORT_HIST, 0.0, seg_tiles_kernel, (u32)ceil_div(grid2, 256), 256, 0, m_boff, m_tstart, ptile, (u32)grid2, tinfo);
         c.check(cudaMemsetAsync(status, 0, grid2 * kRadixSize * stw, st));
-        if (pipe & 2) launch_part_pipe<ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
+        // second level: only the key bits below the bucket prefix are written when they fit 32 bits (bucket_load_key)
+        int k32 = (pipe & 2) && K - 16 + key_shift <= 32;
+        { const char *env = getenv("LIBSAIS_CUDA_MSD_K32"); if (env && *env && atoi(env) == 0) k32 = 0; }
+        pa.out32 = k32;
+        if (pipe & 2) launch_part_pipe<ArraySrc, true>(c, KC_PART_PASS, (double)n * (k32 ? 20.0 : 24.0), ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
         else launch_part_pass<u64, u32, ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
         LSC_LAUNCH(c, KC_SORT_HIST, 0.0, bucket_tiles_kernel, (u32)ceil_div(btiles, 256), 256, 0, m_boff, btiles, Cw, tb);
         c.check(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
-        LSC_LAUNCH(c, KC_BUCKET_SORT, (double)n * 24.0, bucket_sort_kernel, (u32)btiles, kBucketThreads, sizeof(BucketSmem),
-                   keyB, valB, tb, n, Cw, key_shift, K - 16, keyA, valA, err);
+        // fused rank stage: the sorted keys are never written; positions go straight to the suffix array (or valA)
+        { const char *env = getenv("LIBSAIS_CUDA_MSD_FUSE"); msd_fused = !(env && *env && atoi(env) == 0); }
+        BucketFuse fz; fz.on = msd_fused ? 1 : 0; fz.masks = rmasks; fz.rows = bwt_mode ? opt.bwt_rows : nullptr;
+        fz.tail_start = n >= (u64)k ? n - (u64)k + 1 : 0;
+        fz.aux_I = opt.aux_I; fz.aux_mask = opt.aux_I ? opt.aux_r - 1 : 0; fz.aux_shift = opt.aux_I ? bits_for(opt.aux_r) - 1 : 0;
+        fz.primary = c.d_scalars + S_PRIMARY;
+        if (msd_fused) c.check(cudaMemsetAsync(rmasks, 0, ceil_div(n, 16) * sizeof(u32), st));
+        LSC_LAUNCH(c, KC_BUCKET_SORT, (double)n * ((k32 ? 8.0 : 12.0) + (msd_fused ? 4.0 + (bwt_mode ? 1.0 : 0.0) + 0.25 : 12.0)), bucket_sort_kernel, (u32)btiles, kBucketThreads, sizeof(BucketSmem),
+                   keyB, valB, tb, n, Cw, key_shift, K - 16, keyA, (msd_fused && SA) ? SA : valA, err, fz, m_boff, k32);
         rs.passes = 2;
         where = c.failed() ? -1 : 0;
     } else if (fuse_keys) {
@@ -904,6 +947,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     }
     if (where < 0) return -2;
     u64 *ks = where ? keyB : keyA; u32 *vs = where ? valB : valA;      // S0: sorted round-0 (key, pos)
+    u32 *const vbuf = vs;                                               // the arena buffer (ping-pong half of the later rounds)
+    if (msd_fused && SA) vs = SA;                                       // fused MSD path: the positions in slot order went straight to SA
     u64 *ko = where ? keyA : keyB; u32 *vo = where ? valA : valB;
     u32 *slot_cur = a_slot0, *slot_nxt = a_slot1;
     const u64 tail_start = n >= (u64)k ? n - (u64)k + 1 : 0;
@@ -919,7 +964,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     ra.masks = rmasks; ra.wagg = rwagg; ra.tagg = rtagg; ra.nchunks = ceil_div(n, 32);
     ra.ntiles = rank_tiles; ra.out_counts = c.d_scalars + S_NACT;
     ra.pair_idx = nullptr; ra.pair_val = nullptr; ra.phist = nullptr; ra.pshift = 0;
-    LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
+    if (msd_fused) LSC_LAUNCH(c, KC_RANK_INIT, (double)n * 0.25, rank_agg_kernel, (u32)rank_tiles, kRankThreads, 0, rmasks, n, rwagg, rtagg, rank_tiles);
+    else LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
     LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
     if (!read_round_scalars(c)) return -2;
     u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
@@ -930,12 +976,12 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     // the rare look-ups that hit one recompute it by binary search in the sorted round-0 keys.
     bool lazy = N * 32 <= n;
     { const char *env = getenv("LIBSAIS_CUDA_LAZY_ISA"); if (env && *env) lazy = atoi(env) != 0; }
-    u64 *rk0 = ks, *rk1 = ko; u32 *rv0 = vs, *rv1 = vo;
+    u64 *rk0 = ks, *rk1 = ko; u32 *rv0 = vbuf, *rv1 = vo;
     if (N > 0) {
         if (lazy) {
             rk0 = c.alloc_n<u64>(N); rk1 = c.alloc_n<u64>(N); rv0 = c.alloc_n<u32>(N); rv1 = c.alloc_n<u32>(N);
             if (!rv1 || !rk1 || !rk0 || !rv0) {                 // no room for separate buffers: fall back to the full ISA
-                lazy = false; rk0 = ks; rk1 = ko; rv0 = vs; rv1 = vo; c.last_error = cudaSuccess;
+                lazy = false; rk0 = ks; rk1 = ko; rv0 = vbuf; rv1 = vo; c.last_error = cudaSuccess;
             }
         }
         if (lazy) {
@@ -950,7 +996,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             ra.phist = nullptr;
         }
     }
-    LazyArgs la; la.words = words; la.b = b; la.K = K; la.s0_keys = ks; la.s0_pos = vs; la.key_shift = key_shift;
+    LazyArgs la; la.words = words; la.b = b; la.K = K; la.s0_keys = msd_fused ? nullptr : ks; la.s0_pos = vs; la.key_shift = key_shift;
     la.tail_start = tail_start; la.n = n;
 
     // ---- doubling rounds on the active suffixes
@@ -962,7 +1008,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     bool local_on = true;
     { const char *env = getenv("LIBSAIS_CUDA_LOCAL_SORT"); if (env && *env) local_on = atoi(env) != 0; }
     local_on = local_on && !lazy;
-    const u64 kLocalMin = (u64)1 << 18;
+    u64 kLocalMin = (u64)1 << 18;
+    { const char *env = getenv("LIBSAIS_CUDA_LOCAL_MIN"); if (env && *env && atoi(env) > 0) kLocalMin = (u64)atoi(env); }      // tests: small texts through the local paths
     auto launch_big_check = [&](u64 n_upper) {
         c.check(cudaMemsetAsync(c.d_scalars + S_BIGGRP, 0, sizeof(u64), st));
         const u64 want = ceil_div(n_upper, 256 * 8);
@@ -982,6 +1029,51 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         launch_big_check(N);
         if (!read_round_scalars(c)) return -2;
         win = local_window();
+    }
+    // ---- position-ordered rounds (po_rounds.cuh): no group larger than kPoMaxGroup and enough suffixes left to pay for
+    // the one-time reordering of the groups.  From here on the active record is (position, rank of the group).
+    int po_env = 1;
+    { const char *env = getenv("LIBSAIS_CUDA_PO"); if (env && *env) po_env = atoi(env); }
+    if (po_env && local_on && N >= kLocalMin && !(c.h_scalars[S_BIGGRP] & 4)) {
+        const u64 f = c.h_scalars[S_BIGGRP];
+        const u32 limit = !(f & 1) ? kLocalCountLimit : !(f & 2) ? 512u : kPoMaxGroup;
+        const u32 C = (u32)kPoCap - limit;
+        // groups sorted by the position of their head suffix (stable: members stay in slot order)
+        u32 *head_pos = a_slot1, *head_slot = a_slot1 + G;
+        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * 8 + (double)G * 8, po_heads_kernel, (u32)ceil_div(N, 256), 256, 0, a_pos, a_grp, slot_cur, N, head_pos, head_slot);
+        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (8 + 12), po_keys_kernel, (u32)ceil_div(N, 256), 256, 0, a_pos, a_grp, head_pos, head_slot, N, keyA, valA);
+        const int pos_bits = bits_for(n - 1);
+        int drop = pos_bits > 24 ? pos_bits - 24 : 0;                 // 3 digit passes: groups whose heads share the dropped low bits stay in slot order
+        { const char *env = getenv("LIBSAIS_CUDA_PO_DROP"); if (env && *env) { drop = atoi(env); if (drop < 0) drop = 0; if (drop >= pos_bits) drop = pos_bits - 1; } }
+        RoundStat r0; r0.h = h; r0.n_active = N; r0.n_groups = G; r0.passes = 0; r0.key_bits = pos_bits - drop;
+        where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, N, 32 + drop, 32 + pos_bits, sort_temp, err, &r0.passes);
+        if (where < 0) return -2;
+        const u64 *kv_k = where ? keyB : keyA; const u32 *kv_v = where ? valB : valA;
+        u32 *pair = (u32 *)(where ? keyA : keyB);
+        u32 *lp[2] = {a_pos, a_slot0}, *lr[2] = {a_grp, a_slot1};
+        int cur = 0; bool first = true;
+        while (N > 0) {
+            if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
+            RoundStat r; r.h = h; r.n_active = N; r.key_bits = rank_bits + 11; r.passes = first ? r0.passes : 0; r.n_groups = 0;
+            const u64 tiles = ceil_div(N, (u64)C);
+            c.check(cudaMemsetAsync(sort_temp, 0, tiles * sizeof(u64), st));
+            c.check(cudaMemsetAsync(c.d_scalars + S_TICKET, 0, sizeof(u64), st));
+            c.check(cudaMemsetAsync(c.d_scalars + S_NACT, 0, 2 * sizeof(u64), st));
+            PoArgs pa; pa.kv_keys = kv_k; pa.kv_vals = kv_v; pa.a_pos = lp[cur ^ 1]; pa.a_rank = lr[cur ^ 1];
+            pa.N = N; pa.n = n; pa.h = h; pa.C = C; pa.ISA = ISA; pa.o_pos = lp[cur]; pa.o_rank = lr[cur];
+            pa.pair_pos = pair; pa.pair_rank = pair + N;
+            pa.SA = SA; pa.rows = bwt_mode ? opt.bwt_rows : nullptr; pa.text = bwt_mode ? (const u8 *)d_T : nullptr;
+            pa.aux_mask = ra.aux_mask; pa.aux_shift = ra.aux_shift; pa.aux_I = opt.aux_I; pa.primary = c.d_scalars + S_PRIMARY;
+            pa.status = (u64 *)sort_temp; pa.ticket = (u32 *)(c.d_scalars + S_TICKET); pa.out_counts = c.d_scalars + S_NACT; pa.err = err;
+            if (first) LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (12 + 4 + 8 + 8), po_round_kernel<true>, (u32)tiles, kPoThreads, 0, pa);
+            else       LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (8 + 4 + 8 + 8), po_round_kernel<false>, (u32)tiles, kPoThreads, 0, pa);
+            LSC_LAUNCH(c, KC_SCATTER, (double)N * 12, po_apply_kernel, (u32)ceil_div(N, 256), 256, 0, pa.pair_pos, pa.pair_rank, N, ISA);
+            if (!read_round_scalars(c)) return -2;
+            N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
+            r.n_groups = G;
+            c.rounds.push_back(r);
+            first = false; cur ^= 1; h *= 2; ++round;
+        }
     }
     while (N > 0) {
         if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }

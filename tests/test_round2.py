@@ -231,3 +231,42 @@ def test_unbwt_aux_uses_the_samples(cu):
     got = cu.unbwt_aux(U, r, J)
     want = T.copy(); want[r:2 * r], want[2 * r:3 * r] = T[2 * r:3 * r], T[r:2 * r]
     assert got[0] == 0 and (got[1] == want).all()
+
+
+def test_position_ordered_rounds(cu):
+    """Rounds >= 1 on the position-ordered active list (po_rounds.cuh) against the slot-ordered rounds of round 1
+    and the oracle: mutated copies (groups of `copies` suffixes that take many rounds), exact repeats (ties that
+    only the end of the text breaks), runs, texts whose groups straddle the 128 / 512 / 1024 limits, small lists
+    (LIBSAIS_CUDA_LOCAL_MIN lowers the threshold so short texts take the path), every key-drop of the group sort.
+    SA, BWT + primary index and the aux samples must be bit-exact."""
+    o = _best_cpu()
+    rng = np.random.default_rng(2024)
+    texts = {"copies100": gen.repetitive_dna(20_000, 100), "copies7": gen.repetitive_dna(150_000, 7, rate_num=300),
+             "copies130": gen.repetitive_dna(3_000, 130), "copies600": gen.repetitive_dna(1_500, 600, rate_num=4000),
+             "copies1000": gen.repetitive_dna(700, 1000, rate_num=8000),
+             "exact_repeats": np.tile(gen.dna(5, 30_000), 9), "tail_repeat": np.concatenate([gen.dna(6, 100_000), gen.dna(6, 100_000)[:70_000]]),
+             "bytes_copies": np.tile(gen.rand_bytes(4, 50_000), 4), "runs": np.repeat(gen.dna(8, 40_000), 5),
+             "small": gen.repetitive_dna(300, 20), "binary": (rng.integers(0, 2, 300_000) + 48).astype(np.uint8)}
+    texts["mutated_bytes"] = texts["bytes_copies"].copy()
+    texts["mutated_bytes"][rng.integers(0, len(texts["mutated_bytes"]), 300)] = 7
+    knobs = ("LIBSAIS_CUDA_PO", "LIBSAIS_CUDA_LOCAL_MIN", "LIBSAIS_CUDA_PO_DROP")
+    try:
+        for name, T in texts.items():
+            rs, SAr = o.sa(T)
+            rb, Ur = o.bwt(T)
+            Ir = o.bwt_aux(T, 128)[2]
+            for po, lmin, drop in (("1", "1", None), ("1", "1", "0"), ("1", "4096", "9"), ("0", "1", None)):
+                for k in knobs:
+                    os.environ.pop(k, None)
+                os.environ["LIBSAIS_CUDA_PO"] = po; os.environ["LIBSAIS_CUDA_LOCAL_MIN"] = lmin
+                if drop is not None:
+                    os.environ["LIBSAIS_CUDA_PO_DROP"] = drop
+                rc, SA = cu.sa(T)
+                assert rc == 0 and (SA == SAr).all(), (name, po, lmin, drop)
+                rcb, U = cu.bwt(T)
+                assert rcb == rb and (U == Ur).all(), (name, po, lmin, drop)
+                _, U2, I = cu.bwt_aux(T, 128)
+                assert (U2 == Ur).all() and (I == Ir).all(), (name, po, lmin, drop)
+    finally:
+        for k in knobs:
+            os.environ.pop(k, None)

@@ -78,6 +78,8 @@ def run(name):
         T = gen.repetitive_dna(1_900_000, 100); what = ("sa", "plcp", "lcp", "bwt")
     elif name == "c3":
         T = gen.repetitive_dna(19_000_000, 100); what = ("sa", "plcp", "lcp")
+    elif name == "c3d":                                      # config 3 at full size, generated on the device (SA only: the rounds)
+        T = None; what = ("sa",)
     elif name == "c5lite":
         return run_c5lite()
     elif name == "c4b":
@@ -89,9 +91,13 @@ def run(name):
         T = np.frombuffer(b" ".join(words[i] for i in idx), dtype=np.uint8).copy(); what = ("sa", "plcp", "bwt")
     else:
         raise SystemExit("unknown config " + name)
-    n = len(T)
+    if T is None:
+        dT = gen.repetitive_dna_torch(19_000_000, 100)
+        torch.cuda.synchronize(); torch.cuda.empty_cache()
+    else:
+        dT = torch.from_numpy(T).cuda()
+    n = dT.numel()
     out["n"] = n; out["gen_s"] = round(time.time() - t0, 1)
-    dT = torch.from_numpy(T).cuda()
     dSA = None
     for w in what:
         if w == "sa":
