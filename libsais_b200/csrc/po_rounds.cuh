@@ -40,6 +40,7 @@ struct PoArgs {
     const u64 *kv_keys; const u32 *kv_vals;      // first round: rank = low word of kv_keys[j], position = kv_vals[j] (output of the group sort)
     const u32 *a_pos, *a_rank;                   // later rounds
     u64 N, n, h; u32 C;                          // list length, text length, sorted prefix length, window of a tile
+    int bin_shift;                               // rank updates of a tile are grouped by (position >> bin_shift) & 255
     const u32 *ISA;
     u32 *o_pos, *o_rank;                         // suffixes that stay active
     u32 *pair_pos, *pair_rank;                   // [N] rank updates (kPoNone: none)
@@ -78,21 +79,37 @@ __device__ __forceinline__ void po_block_scan(u32 mymax, u32 mysum, u32 &exmax, 
     __syncthreads();
 }
 
+// c += (x <= r) / (x < r), as one compare on the integer pipe and one predicated add on the FMA pipe (float counter,
+// exact below 2^24).  Left to itself the compiler spends two integer-pipe instructions and a move per pair, and the
+// integer pipe is what bounds the ordering step (one warp instruction per two cycles: profiles/po_rounds_r2.md).
+__device__ __forceinline__ void po_cnt_le(float &c, u32 x, u32 r)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p add.f32 %0, %0, 0f3F800000;\n\t}" : "+f"(c) : "r"(x), "r"(r));
+}
+__device__ __forceinline__ void po_cnt_lt(float &c, u32 x, u32 r)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.f32 %0, %0, 0f3F800000;\n\t}" : "+f"(c) : "r"(x), "r"(r));
+}
+
+static const int kPoItems = kPoCap / kPoIPT + kPoCap / 2;   // work items of the ordering step: <= cnt/8 + (groups <= cnt/2)
+
 template <bool KV>
 __global__ void __launch_bounds__(kPoThreads, 4)
 po_round_kernel(const PoArgs a)
 {
-    __shared__ __align__(16) u64 comp[kPoCap];   // gathered rank, then (group start << 43 | rank << 11 | index); after the counting: sorted ranks, then new ranks (u32 view)
-    __shared__ __align__(16) u32 s_p[kPoCap];    // positions: list order, then sorted order
+    __shared__ __align__(16) u32 s_r[kPoCap];    // gathered rank + 1 by list index; after the ranking: new rank by sorted index
+    __shared__ __align__(16) u32 s_p[kPoCap];    // position by list index
     __shared__ __align__(16) u32 s_rk[kPoCap];   // rank of the element's group (the same for every index of a group)
     __shared__ __align__(16) unsigned short s_gs[kPoCap];   // index of the first element of the group
     __shared__ __align__(16) unsigned short s_ge[kPoCap];   // at a group's first index: one past its last; after the ranking: output offset | flags
+    __shared__ __align__(16) unsigned short s_src[kPoCap];  // sorted index -> list index
+    __shared__ __align__(16) unsigned short s_item[kPoItems];   // work item -> first list index of its (up to) 8 elements; later s_bin
+    __shared__ __align__(16) u32 s_out[kPoCap];  // rank updates of the tile, staged in bin order (positions reuse s_rk)
     __shared__ u32 s_scan[2][kPoWarps];
     __shared__ u32 bounds[2];
     __shared__ u32 s_tile;
     __shared__ u64 s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    u32 *s_r2 = reinterpret_cast<u32 *>(comp);
 
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
     if (tid < 2) bounds[tid] = 0xFFFFFFFFu;
@@ -120,8 +137,9 @@ po_round_kernel(const PoArgs a)
     const u32 cnt = ok ? bounds[1] - bounds[0] : 0;
     const u64 s = t0 + (ok ? bounds[0] : 0);
 
-    u32 total = 0, act_groups = 0;
-    u32 e_excl[kPoIPT];                          // phase "emit" state of my 8 sorted elements
+    u32 total = 0, act_groups = 0, nchanged = 0;
+    u32 lr[kPoIPT];                              // rank of my (strided) elements inside their update bin
+    u32 *s_bin = reinterpret_cast<u32 *>(s_item);
     if (cnt) {                                   // uniform over the CTA
         // ---- gather (strided: coalesced list loads, 8 look-ups in flight per thread)
         {
@@ -141,19 +159,20 @@ po_round_kernel(const PoArgs a)
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
                 const u32 idx = i * kPoThreads + tid;
-                if (idx < cnt) { s_p[idx] = p[i]; s_rk[idx] = rk[i]; comp[idx] = (u64)r[i]; }
+                if (idx < cnt) { s_p[idx] = p[i]; s_rk[idx] = rk[i]; s_r[idx] = r[i]; }
             }
         }
         __syncthreads();
         const u32 idx0 = (u32)tid * kPoIPT;
         const int nv = idx0 < cnt ? (cnt - idx0 < (u32)kPoIPT ? (int)(cnt - idx0) : kPoIPT) : 0;
-        // ---- group starts (blocked: a thread owns 8 consecutive elements)
+        // ---- group starts and ends (blocked: a thread owns 8 consecutive elements)
+        u32 hm = 0;                              // which of my elements head a group
         {
             u32 rk[kPoIPT];
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) rk[i] = i < nv ? s_rk[idx0 + i] : 0;
             const u32 rprev = (nv && idx0 > 0) ? s_rk[idx0 - 1] : 0;
-            u32 hm = 0, last = 0;
+            u32 last = 0;
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
                 const bool hd = i < nv && (idx0 + i == 0 || rk[i] != (i ? rk[i - 1] : rprev));
@@ -169,45 +188,71 @@ po_round_kernel(const PoArgs a)
                     if ((hm >> i) & 1u) { if (idx > 0) s_ge[cur] = (unsigned short)idx; cur = idx; }
                     s_gs[idx] = (unsigned short)cur;
                     if (idx == cnt - 1) s_ge[cur] = (unsigned short)cnt;
-                    comp[idx] = ((u64)cur << 43) | ((comp[idx] & 0xFFFFFFFFull) << 11) | (u64)idx;
                 }
             }
         }
         __syncthreads();
-        // ---- order: sorted index = elements of the tile with a smaller (group, rank, index) key.  Everything before
-        // the group of my first element is smaller, everything after the group of my last one is larger.
-        u32 d[kPoIPT], pp[kPoIPT], rr[kPoIPT];
+        // ---- work items of the ordering step: a group of s elements is cut into ceil(s / 8) runs of consecutive
+        // elements, one item each, so that the 8 elements of an item always share their group (a thread that owned 8
+        // consecutive elements of the TILE would straddle groups and drag its whole warp through both of them)
+        u32 nitems;
         {
-            u64 c[kPoIPT];
+            u32 mine = 0;
 #pragma unroll
-            for (int i = 0; i < kPoIPT; ++i) { c[i] = i < nv ? comp[idx0 + i] : 0; d[i] = 0; pp[i] = i < nv ? s_p[idx0 + i] : 0; }
-            if (nv) {
-                const u32 lo = (u32)(c[0] >> 43);
-                const u32 hi = s_ge[(u32)(comp[idx0 + nv - 1] >> 43)];
-#pragma unroll 2
-                for (u32 j = lo; j < hi; ++j) {
-                    const u64 x = comp[j];
+            for (int i = 0; i < kPoIPT; ++i)
+                if ((hm >> i) & 1u) mine += ((u32)s_ge[idx0 + i] - (idx0 + i) + kPoIPT - 1) / kPoIPT;
+            u32 dummy, off;
+            po_block_scan(0, mine, dummy, off, nitems, s_scan, lane, warp);
 #pragma unroll
-                    for (int i = 0; i < kPoIPT; ++i) d[i] += (u32)(x < c[i]);
+            for (int i = 0; i < kPoIPT; ++i) {
+                if ((hm >> i) & 1u) {
+                    const u32 g0 = idx0 + i, g1 = s_ge[g0];
+                    for (u32 e = g0; e < g1; e += kPoIPT) s_item[off++] = (unsigned short)e;
                 }
-#pragma unroll
-                for (int i = 0; i < kPoIPT; ++i) d[i] += lo;
             }
-#pragma unroll
-            for (int i = 0; i < kPoIPT; ++i) rr[i] = (u32)(c[i] >> 11);
         }
         __syncthreads();
+        // ---- order: sorted index of an element = group start + members with a smaller rank + members with the same rank in
+        // front of it.  32-bit compares; every loaded rank is compared with the item's 8 elements.
+        for (u32 k = tid; k < nitems; k += kPoThreads) {
+            const u32 e0 = s_item[k], g0 = s_gs[e0], g1 = s_ge[g0];
+            const u32 ne = g1 - e0 < (u32)kPoIPT ? g1 - e0 : (u32)kPoIPT;
+            u32 r[kPoIPT]; float c[kPoIPT];
 #pragma unroll
-        for (int i = 0; i < kPoIPT; ++i) if (i < nv) { s_p[d[i]] = pp[i]; s_r2[d[i]] = rr[i]; }
+            for (int i = 0; i < kPoIPT; ++i) { r[i] = (u32)i < ne ? s_r[e0 + i] : 0xFFFFFFFFu; c[i] = 0.f; }
+#pragma unroll 4
+            for (u32 j = g0; j < e0; ++j) {                       // in front of the item: ties count
+                const u32 x = s_r[j];
+#pragma unroll
+                for (int i = 0; i < kPoIPT; ++i) po_cnt_le(c[i], x, r[i]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < kPoIPT; ++jj) {                 // the item itself
+#pragma unroll
+                for (int i = 0; i < kPoIPT; ++i) {
+                    if (jj < i) po_cnt_le(c[i], r[jj], r[i]);
+                    if (jj > i) po_cnt_lt(c[i], r[jj], r[i]);
+                }
+            }
+#pragma unroll 4
+            for (u32 j = e0 + ne; j < g1; ++j) {                  // behind the item: only smaller ranks count
+                const u32 x = s_r[j];
+#pragma unroll
+                for (int i = 0; i < kPoIPT; ++i) po_cnt_lt(c[i], x, r[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) if ((u32)i < ne) s_src[g0 + (u32)c[i]] = (unsigned short)(e0 + i);
+        }
         __syncthreads();
         // ---- rank (blocked over the sorted order): sub-group heads, finals, new ranks, output offsets
+        s_bin[tid] = 0;                          // (the items are done with)
         {
             u32 r2[kPoIPT + 1]; u32 gs[kPoIPT + 1];
 #pragma unroll
-            for (int i = 0; i < kPoIPT; ++i) { r2[i] = i < nv ? s_r2[idx0 + i] : 0; gs[i] = i < nv ? s_gs[idx0 + i] : 0; }
+            for (int i = 0; i < kPoIPT; ++i) { r2[i] = i < nv ? s_r[s_src[idx0 + i]] : 0; gs[i] = i < nv ? s_gs[idx0 + i] : 0; }
             const bool more = nv == kPoIPT && idx0 + kPoIPT < cnt;
-            r2[kPoIPT] = more ? s_r2[idx0 + kPoIPT] : 0; gs[kPoIPT] = more ? s_gs[idx0 + kPoIPT] : 0;
-            const u32 r2prev = (nv && idx0 > 0) ? s_r2[idx0 - 1] : 0;
+            r2[kPoIPT] = more ? s_r[s_src[idx0 + kPoIPT]] : 0; gs[kPoIPT] = more ? s_gs[idx0 + kPoIPT] : 0;
+            const u32 r2prev = (nv && idx0 > 0) ? s_r[s_src[idx0 - 1]] : 0;
             u32 nhm = 0, actm = 0, last = 0;
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
@@ -221,11 +266,10 @@ po_round_kernel(const PoArgs a)
                 }
             }
             u32 carry, excl;
-            po_block_scan(last, (u32)__popc(actm), carry, excl, total, s_scan, lane, warp);
+            po_block_scan(last, (u32)__popc(actm), carry, excl, total, s_scan, lane, warp);   // (its barriers: every gathered rank has been read)
             u32 cur = carry;
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
-                e_excl[i] = 0;
                 if (i < nv) {
                     const u32 dd = idx0 + i;
                     if ((nhm >> i) & 1u) cur = dd;
@@ -234,9 +278,27 @@ po_round_kernel(const PoArgs a)
                     act_groups += (u32)(act && ((nhm >> i) & 1u));
                     // offset among the tile's actives (< 2048: 11 bits) | active << 14 | rank changed << 15
                     s_ge[dd] = (unsigned short)((excl + (u32)__popc(actm & ((1u << i) - 1u))) | (act ? 1u << 14 : 0u) | (cur != gs[i] ? 1u << 15 : 0u));
-                    s_r2[dd] = newrank;
+                    s_r[dd] = newrank;
                 }
             }
+        }
+        __syncthreads();
+        // ---- the rank updates leave the tile grouped by text neighbourhood: neighbouring groups of a repetitive text
+        // update neighbouring ISA entries (copy by copy), and a warp of po_apply_kernel that holds 32 updates of one
+        // neighbourhood stores into a few sectors instead of 32 (the scattered 4-byte stores, not the bytes, bound that
+        // kernel: 50 G stores/s, profiles/po_rounds_r2.md).  One shared atomic per update.
+#pragma unroll
+        for (int i = 0; i < kPoIPT; ++i) {
+            const u32 dd = i * kPoThreads + tid;
+            lr[i] = 0;
+            if (dd < cnt && (s_ge[dd] >> 15)) lr[i] = atomicAdd(&s_bin[(s_p[s_src[dd]] >> a.bin_shift) & 255u], 1u);
+        }
+        __syncthreads();
+        {
+            const u32 c = s_bin[tid];
+            u32 dummy, ex;
+            po_block_scan(0, c, dummy, ex, nchanged, s_scan, lane, warp);
+            s_bin[tid] = ex;
         }
     }
     // ---- chained scan over the tiles: where this tile's active suffixes go
@@ -282,10 +344,12 @@ po_round_kernel(const PoArgs a)
     for (int i = 0; i < kPoIPT; ++i) {
         const u32 dd = i * kPoThreads + tid;
         if (dd < cnt) {
-            const u32 p = s_p[dd], meta = s_ge[dd], newrank = s_r2[dd];
+            const u32 p = s_p[s_src[dd]], meta = s_ge[dd], newrank = s_r[dd];
             const bool act = (meta >> 14) & 1u, changed = (meta >> 15) & 1u;
-            a.pair_pos[s + dd] = changed ? p : kPoNone;
-            a.pair_rank[s + dd] = newrank;
+            if (changed) {
+                const u32 slot = s_bin[(p >> a.bin_shift) & 255u] + lr[i];
+                s_rk[slot] = p; s_out[slot] = newrank;           // (the group ranks in s_rk are done with)
+            }
             if (act) {
                 const u64 o = base + (meta & 0x3FFFu);
                 a.o_pos[o] = p; a.o_rank[o] = newrank;
@@ -298,16 +362,40 @@ po_round_kernel(const PoArgs a)
             }
         }
     }
+    __syncthreads();
+    for (u32 idx = tid; idx < cnt; idx += kPoThreads) {           // coalesced: the tile's updates, then "none"
+        const bool have = idx < nchanged;
+        a.pair_pos[s + idx] = have ? s_rk[idx] : kPoNone;
+        if (have) a.pair_rank[s + idx] = s_out[idx];
+    }
 }
 
-// ISA[p] = rank for the pairs of the round (after the round kernel: the round reads the previous ranks)
+// ISA[p] = rank for the pairs of the round (after the round kernel: the round reads the previous ranks).
+// CTA b takes the 2048 consecutive pairs [2048 b, ...): CTAs are dispatched in index order, so the updates of neighbouring
+// tiles -- neighbouring ISA entries -- are in flight together and merge in L2 (a grid-stride variant that spread a CTA's
+// pairs over the whole list lost that: 26 -> 38 ms per round).  Both 16-byte loads of a quad are issued before its stores.
 static __global__ void __launch_bounds__(256)
 po_apply_kernel(const u32 *__restrict__ pair_pos, const u32 *__restrict__ pair_rank, u64 N, u32 *__restrict__ ISA)
 {
-    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
-    if (j >= N) return;
-    const u32 p = ld_stream(pair_pos + j);
-    if (p != kPoNone) ISA[p] = ld_stream(pair_rank + j);
+    const u64 base = (u64)blockIdx.x * 2048;
+    const bool vec = (((uintptr_t)pair_pos | (uintptr_t)pair_rank) & 15) == 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const u64 j = base + ((u64)k * 256 + threadIdx.x) * 4;
+        if (j >= N) return;
+        if (vec && j + 4 <= N) {
+            const uint4 p = *reinterpret_cast<const uint4 *>(pair_pos + j), r = *reinterpret_cast<const uint4 *>(pair_rank + j);
+            if (p.x != kPoNone) ISA[p.x] = r.x;
+            if (p.y != kPoNone) ISA[p.y] = r.y;
+            if (p.z != kPoNone) ISA[p.z] = r.z;
+            if (p.w != kPoNone) ISA[p.w] = r.w;
+        } else {
+            for (u64 i = j; i < j + 4 && i < N; ++i) {
+                const u32 p = pair_pos[i];
+                if (p != kPoNone) ISA[p] = pair_rank[i];
+            }
+        }
+    }
 }
 
 // ---- the one-time reordering of the groups by the text position of their head suffix

@@ -1045,6 +1045,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         const int pos_bits = bits_for(n - 1);
         int drop = pos_bits > 24 ? pos_bits - 24 : 0;                 // 3 digit passes: groups whose heads share the dropped low bits stay in slot order
         { const char *env = getenv("LIBSAIS_CUDA_PO_DROP"); if (env && *env) { drop = atoi(env); if (drop < 0) drop = 0; if (drop >= pos_bits) drop = pos_bits - 1; } }
+        int bin_shift = 7;
+        { const char *env = getenv("LIBSAIS_CUDA_PO_BIN"); if (env && *env) { bin_shift = atoi(env); if (bin_shift < 0) bin_shift = 0; if (bin_shift > 24) bin_shift = 24; } }
         RoundStat r0; r0.h = h; r0.n_active = N; r0.n_groups = G; r0.passes = 0; r0.key_bits = pos_bits - drop;
         where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, N, 32 + drop, 32 + pos_bits, sort_temp, err, &r0.passes);
         if (where < 0) return -2;
@@ -1060,14 +1062,14 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             c.check(cudaMemsetAsync(c.d_scalars + S_TICKET, 0, sizeof(u64), st));
             c.check(cudaMemsetAsync(c.d_scalars + S_NACT, 0, 2 * sizeof(u64), st));
             PoArgs pa; pa.kv_keys = kv_k; pa.kv_vals = kv_v; pa.a_pos = lp[cur ^ 1]; pa.a_rank = lr[cur ^ 1];
-            pa.N = N; pa.n = n; pa.h = h; pa.C = C; pa.ISA = ISA; pa.o_pos = lp[cur]; pa.o_rank = lr[cur];
-            pa.pair_pos = pair; pa.pair_rank = pair + N;
+            pa.N = N; pa.n = n; pa.h = h; pa.C = C; pa.bin_shift = bin_shift; pa.ISA = ISA; pa.o_pos = lp[cur]; pa.o_rank = lr[cur];
+            pa.pair_pos = pair; pa.pair_rank = where ? valA : valB;                  // both 16-byte aligned (po_apply_kernel)
             pa.SA = SA; pa.rows = bwt_mode ? opt.bwt_rows : nullptr; pa.text = bwt_mode ? (const u8 *)d_T : nullptr;
             pa.aux_mask = ra.aux_mask; pa.aux_shift = ra.aux_shift; pa.aux_I = opt.aux_I; pa.primary = c.d_scalars + S_PRIMARY;
             pa.status = (u64 *)sort_temp; pa.ticket = (u32 *)(c.d_scalars + S_TICKET); pa.out_counts = c.d_scalars + S_NACT; pa.err = err;
             if (first) LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (12 + 4 + 8 + 8), po_round_kernel<true>, (u32)tiles, kPoThreads, 0, pa);
             else       LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (8 + 4 + 8 + 8), po_round_kernel<false>, (u32)tiles, kPoThreads, 0, pa);
-            LSC_LAUNCH(c, KC_SCATTER, (double)N * 12, po_apply_kernel, (u32)ceil_div(N, 256), 256, 0, pa.pair_pos, pa.pair_rank, N, ISA);
+            LSC_LAUNCH(c, KC_SCATTER, (double)N * 12, po_apply_kernel, (u32)ceil_div(N, 2048), 256, 0, pa.pair_pos, pa.pair_rank, N, ISA);
             if (!read_round_scalars(c)) return -2;
             N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
             r.n_groups = G;

@@ -30,5 +30,10 @@ if "c3s" in which:
     assert ctx.lcp_dev(dP.data_ptr(), dSA.data_ptr(), dL.data_ptr(), n) == 0
     pr = ctx.bwt_dev(dT.data_ptr(), dU.data_ptr(), n)
     assert pr > 0 and ctx.unbwt_dev(dU.data_ptr(), dB.data_ptr(), n, pr) == 0
+if "c3d" in which:                                  # config 3 at full size, SA only (the doubling rounds)
+    dT = gen.repetitive_dna_torch(19_000_000, 100)
+    n = dT.numel()
+    dSA = torch.empty(n, dtype=torch.int32, device="cuda")
+    assert ctx.sa_dev(dT.data_ptr(), dSA.data_ptr(), n) == 0
 torch.cuda.synchronize()
 print("prof_kernels done")
