@@ -41,6 +41,7 @@ struct PoArgs {
     const u32 *a_pos, *a_rank;                   // later rounds
     u64 N, n, h; u32 C;                          // list length, text length, sorted prefix length, window of a tile
     int bin_shift;                               // rank updates of a tile are grouped by (position >> bin_shift) & 255
+    u32 ntiles;                                  // tiles of the round (= CTAs)
     const u32 *ISA;
     u32 *o_pos, *o_rank;                         // suffixes that stay active
     u32 *pair_pos, *pair_rank;                   // [N] rank updates (kPoNone: none)
@@ -111,6 +112,8 @@ po_round_kernel(const PoArgs a)
     __shared__ u64 s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // One tile per CTA.  (A persistent variant -- CTAs drawing tickets until they run out, so that a tile's stores drain under
+    // the next tile's gather instead of on EXIT, where a fifth of the warp samples sit -- was slower: 58 -> 63 ms per round.)
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
     if (tid < 2) bounds[tid] = 0xFFFFFFFFu;
     __syncthreads();
@@ -333,7 +336,7 @@ po_round_kernel(const PoArgs a)
         }
         if (lane == 0) {
             s_base = excl;
-            if (tile == gridDim.x - 1) a.out_counts[0] = excl + total;
+            if (tile == a.ntiles - 1) a.out_counts[0] = excl + total;
         }
     }
     __syncthreads();
@@ -398,28 +401,104 @@ po_apply_kernel(const u32 *__restrict__ pair_pos, const u32 *__restrict__ pair_r
     }
 }
 
-// ---- the one-time reordering of the groups by the text position of their head suffix
-// table of the group heads: position and slot (dense group ids from the rank stage of round 0)
+// ---- the one-time reordering of the GROUPS by the text position of their head suffix.  Whole groups move, so the
+// groups are sorted (one (head position, group) pair per group -- 1/100 of the suffixes in a 100-copy collection),
+// their new starts are the exclusive scan of their sizes in sorted order, and one pass copies every member to
+// new start + offset in the group.  (A sort of the member records themselves cost 4 digit passes over 12-byte
+// records: 87 ms of config 3's 567.)
+// table of the groups from the slot-ordered active list of round 0 (dense, ascending group ids): first list index,
+// head position (the sort key), head slot (= rank of the group), identity (the sort's value)
 static __global__ void __launch_bounds__(256)
-po_heads_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp, const u32 *__restrict__ a_slot, u64 N,
-                u32 *__restrict__ head_pos, u32 *__restrict__ head_slot)
+po_group_table_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp, const u32 *__restrict__ a_slot, u64 N,
+                      u32 *__restrict__ gstart, u32 *__restrict__ ghead_pos, u32 *__restrict__ ghead_slot, u32 *__restrict__ gid)
 {
     const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
     if (j >= N) return;
     const u32 g = a_grp[j];
-    if (j == 0 || a_grp[j - 1] != g) { head_pos[g] = a_pos[j]; head_slot[g] = a_slot[j]; }
+    if (j == 0 || a_grp[j - 1] != g) { gstart[g] = (u32)j; ghead_pos[g] = a_pos[j]; ghead_slot[g] = a_slot[j]; gid[g] = g; }
+    if (j == N - 1) gstart[g + 1] = (u32)N;
 }
 
-// sort key (head position << 32 | head slot = rank of the group), value = position
+static const int kPoScanThreads = 512;
+static const int kPoScanChunk = kPoScanThreads * 8;
+// sum of the sizes of the groups sg[i], i in chunk b
+static __global__ void __launch_bounds__(kPoScanThreads)
+po_scan_sums_kernel(const u32 *__restrict__ sg, const u32 *__restrict__ gstart, u64 G, u32 *__restrict__ bsum)
+{
+    __shared__ u32 s_w[kPoScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 base = (u64)blockIdx.x * kPoScanChunk;
+    u32 sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const u64 i = base + (u64)k * kPoScanThreads + tid;
+        if (i < G) { const u32 g = sg[i]; sum += gstart[g + 1] - gstart[g]; }
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (lane == 0) s_w[warp] = sum;
+    __syncthreads();
+    if (tid == 0) { u32 t = 0; for (int w = 0; w < kPoScanThreads / 32; ++w) t += s_w[w]; bsum[blockIdx.x] = t; }
+}
+// one CTA: exclusive scan of the chunk sums in place
+static __global__ void __launch_bounds__(1024)
+po_scan_top_kernel(u32 *__restrict__ bsum, u64 nb)
+{
+    __shared__ u32 s_w[32];
+    __shared__ u32 s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (u64 base = 0; base < nb; base += 1024) {
+        const u64 i = base + tid;
+        const u32 v = i < nb ? bsum[i] : 0;
+        u32 x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        u32 before = s_carry;
+        for (int w = 0; w < warp; ++w) before += s_w[w];
+        if (i < nb) bsum[i] = before + x - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = before + x;
+        __syncthreads();
+    }
+}
+// newstart[sg[i]] = exclusive prefix of the sizes in sorted order (thread: 8 consecutive groups)
+static __global__ void __launch_bounds__(kPoScanThreads)
+po_scan_apply_kernel(const u32 *__restrict__ sg, const u32 *__restrict__ gstart, u64 G, const u32 *__restrict__ bsum, u32 *__restrict__ newstart)
+{
+    __shared__ u32 s_w[kPoScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 i0 = (u64)blockIdx.x * kPoScanChunk + (u64)tid * 8;
+    u32 g[8], sz[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        g[k] = 0; sz[k] = 0;
+        if (i0 + k < G) { g[k] = sg[i0 + k]; sz[k] = gstart[g[k] + 1] - gstart[g[k]]; }
+        sum += sz[k];
+    }
+    u32 x = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    u32 run = bsum[blockIdx.x] + x - sum;
+    for (int w = 0; w < warp; ++w) run += s_w[w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (i0 + k < G) newstart[g[k]] = run; run += sz[k]; }
+}
+// every member to its group's new start + its offset in the group; the record becomes (position, rank of the group)
 static __global__ void __launch_bounds__(256)
-po_keys_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp, const u32 *__restrict__ head_pos,
-               const u32 *__restrict__ head_slot, u64 N, u64 *__restrict__ keys, u32 *__restrict__ vals)
+po_move_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp, u64 N, const u32 *__restrict__ gstart,
+               const u32 *__restrict__ newstart, const u32 *__restrict__ ghead_slot, u32 *__restrict__ o_pos, u32 *__restrict__ o_rank)
 {
     const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
     if (j >= N) return;
     const u32 g = a_grp[j];
-    keys[j] = ((u64)head_pos[g] << 32) | (u64)head_slot[g];
-    vals[j] = a_pos[j];
+    const u64 dst = (u64)newstart[g] + (j - (u64)gstart[g]);
+    o_pos[dst] = a_pos[j];
+    o_rank[dst] = ghead_slot[g];
 }
 
 }  // namespace lsc

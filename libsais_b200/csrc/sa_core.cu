@@ -372,17 +372,23 @@ rank_flags_kernel(const RankArgs a)
     }
 }
 
-// Aggregates of rank_flags from the mask bytes alone (round 0 of the MSD path: bucket_sort_kernel wrote the masks,
-// partition.cuh BucketFuse): per warp and per tile the slot of the last head, the active suffixes, the active groups.
+// Round 0 of the fused MSD path: bucket_sort_kernel (partition.cuh, BucketFuse) left one flag byte per slot (bit 0 head,
+// bit 1 active).  Packs them into rank_flags' mask bytes (heads | actives << 4 per 4 slots) and takes the per-warp and
+// per-tile aggregates: slot of the last head, active suffixes, active groups.
 __global__ void __launch_bounds__(kRankThreads)
-rank_agg_kernel(const u32 *__restrict__ masks, u64 N, u32 *__restrict__ wagg, u32 *__restrict__ tagg, u64 ntiles)
+rank_agg_kernel(const u8 *__restrict__ flags, u32 *__restrict__ masks, u64 N, u32 *__restrict__ wagg, u32 *__restrict__ tagg, u64 ntiles)
 {
     __shared__ u32 s_wagg[3][kRankWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 tile = blockIdx.x;
     const u64 j0 = tile * kRankTile + (u64)tid * 4;
-    const u32 mb = j0 < N ? reinterpret_cast<const u8 *>(masks)[j0 >> 2] : 0u;
-    const u32 h = mb & 15u, am = mb >> 4, gm = am & h;
+    u32 f4 = 0;
+    if (j0 + 4 <= N && ((uintptr_t)flags & 3) == 0) f4 = *reinterpret_cast<const u32 *>(flags + j0);
+    else { for (int i = 0; i < 4; ++i) if (j0 + i < N) f4 |= (u32)flags[j0 + i] << (8 * i); }
+    const u32 h = (f4 & 1u) | ((f4 >> 7) & 2u) | ((f4 >> 14) & 4u) | ((f4 >> 21) & 8u);
+    const u32 am = ((f4 >> 1) & 1u) | ((f4 >> 8) & 2u) | ((f4 >> 15) & 4u) | ((f4 >> 22) & 8u);
+    const u32 gm = am & h;
+    if (j0 < N) reinterpret_cast<u8 *>(masks)[j0 >> 2] = (u8)(h | (am << 4));
     const u32 w_head = __reduce_max_sync(0xffffffffu, h ? (u32)j0 + (u32)(31 - __clz(h)) : 0u);
     const u32 w_act = __reduce_add_sync(0xffffffffu, (u32)__popc(am));
     const u32 w_grp = __reduce_add_sync(0xffffffffu, (u32)__popc(gm));
@@ -707,7 +713,7 @@ size_t sa_workspace_bytes(u64 n, int sym_bytes)
                               + 1);              /* lazy mode: separate small round buffers */
     size_t st = 3 * ceil_div(n, 32) * sizeof(u32) + ceil_div(n, kRankTile) * (kRankWarps + 1) * 3 * sizeof(u32) + 1024;
     size_t msd = (size_t)(65536 + 65540 + 257 + 1024 * 256) * 4 + 256 * 8 + (ceil_div(n, 3072) + 2048) * kRadixSize * 8
-               + (ceil_div(n, 1536) + 2) * 16 + (ceil_div(n, 3072) + 2048) * 8 + 12 * 256;    // round-0 MSD path: prefix histogram, offsets, chunk prefixes, tile status, tile table
+               + (ceil_div(n, 1536) + 2) * 32 + (ceil_div(n, 3072) + 2048) * 8 + 12 * 256;    // round-0 MSD path: prefix histogram, offsets, chunk prefixes, tile status, tile table
     return per + nw * 8 + RadixSort<u64, u32>::temp_bytes(n) + st + msd + 256 + 32 * 256 + 4096;
 }
 
@@ -882,7 +888,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         u32 Cw = (u32)kBucketCap - (u32)m_maxb;
         if (Cw > 6144) Cw = 6144;
         const u64 btiles = ceil_div(n, (u64)Cw);
-        uint4 *tb = c.alloc_n<uint4>(btiles + 1);
+        uint4 *tb = c.alloc_n<uint4>(2 * (btiles + 1));
         uint2 *tinfo = c.alloc_n<uint2>(grid2 + 1);
         if (!status || !tb || !tinfo) return -2;
         u32 *tickets = (u32 *)(c.d_scalars + S_TICKET);
@@ -906,16 +912,25 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         if (pipe & 2) launch_part_pipe<ArraySrc, true>(c, KC_PART_PASS, (double)n * (k32 ? 20.0 : 24.0), ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
         else launch_part_pass<u64, u32, ArraySrc, true>(c, KC_PART_PASS, (double)n * 24.0, ArraySrc(), keyA, valA, keyB, valB, pa, grid2, status);
         LSC_LAUNCH(c, KC_SORT_HIST, 0.0, bucket_tiles_kernel, (u32)ceil_div(btiles, 256), 256, 0, m_boff, btiles, Cw, tb);
-        c.check(cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
         // fused rank stage: the sorted keys are never written; positions go straight to the suffix array (or valA)
         { const char *env = getenv("LIBSAIS_CUDA_MSD_FUSE"); msd_fused = !(env && *env && atoi(env) == 0); }
-        BucketFuse fz; fz.on = msd_fused ? 1 : 0; fz.masks = rmasks; fz.rows = bwt_mode ? opt.bwt_rows : nullptr;
+        BucketFuse fz; fz.on = msd_fused ? 1 : 0; fz.flags = (u8 *)a_slot1; fz.rows = bwt_mode ? opt.bwt_rows : nullptr;      // a_slot1 is idle until the second round
         fz.tail_start = n >= (u64)k ? n - (u64)k + 1 : 0;
         fz.aux_I = opt.aux_I; fz.aux_mask = opt.aux_I ? opt.aux_r - 1 : 0; fz.aux_shift = opt.aux_I ? bits_for(opt.aux_r) - 1 : 0;
         fz.primary = c.d_scalars + S_PRIMARY;
-        if (msd_fused) c.check(cudaMemsetAsync(rmasks, 0, ceil_div(n, 16) * sizeof(u32), st));
-        LSC_LAUNCH(c, KC_BUCKET_SORT, (double)n * ((k32 ? 8.0 : 12.0) + (msd_fused ? 4.0 + (bwt_mode ? 1.0 : 0.0) + 0.25 : 12.0)), bucket_sort_kernel, (u32)btiles, kBucketThreads, sizeof(BucketSmem),
-                   keyB, valB, tb, n, Cw, key_shift, K - 16, keyA, (msd_fused && SA) ? SA : valA, err, fz, m_boff, k32);
+        {
+            const double ab = (double)n * ((k32 ? 8.0 : 12.0) + (msd_fused ? 4.0 + (bwt_mode ? 1.0 : 0.0) + 0.25 : 12.0));
+            u32 *vout = (msd_fused && SA) ? SA : valA;
+#define LSC_BUCKET_SORT(IN32, FUSED)                                                                                                        \
+            do {                                                                                                                            \
+                c.check(cudaFuncSetAttribute(bucket_sort_kernel<IN32, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem))); \
+                LSC_LAUNCH(c, KC_BUCKET_SORT, ab, (bucket_sort_kernel<IN32, FUSED>), (u32)btiles, kBucketThreads, sizeof(BucketSmem),       \
+                           keyB, valB, tb, n, Cw, key_shift, K - 16, keyA, vout, err, fz, m_boff);                                          \
+            } while (0)
+            if (k32) { if (msd_fused) LSC_BUCKET_SORT(true, true); else LSC_BUCKET_SORT(true, false); }
+            else     { if (msd_fused) LSC_BUCKET_SORT(false, true); else LSC_BUCKET_SORT(false, false); }
+#undef LSC_BUCKET_SORT
+        }
         rs.passes = 2;
         where = c.failed() ? -1 : 0;
     } else if (fuse_keys) {
@@ -964,7 +979,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     ra.masks = rmasks; ra.wagg = rwagg; ra.tagg = rtagg; ra.nchunks = ceil_div(n, 32);
     ra.ntiles = rank_tiles; ra.out_counts = c.d_scalars + S_NACT;
     ra.pair_idx = nullptr; ra.pair_val = nullptr; ra.phist = nullptr; ra.pshift = 0;
-    if (msd_fused) LSC_LAUNCH(c, KC_RANK_INIT, (double)n * 0.25, rank_agg_kernel, (u32)rank_tiles, kRankThreads, 0, rmasks, n, rwagg, rtagg, rank_tiles);
+    if (msd_fused) LSC_LAUNCH(c, KC_RANK_INIT, (double)n * 1.25, rank_agg_kernel, (u32)rank_tiles, kRankThreads, 0, (const u8 *)a_slot1, rmasks, n, rwagg, rtagg, rank_tiles);
     else LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
     LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
     if (!read_round_scalars(c)) return -2;
@@ -1038,21 +1053,32 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         const u64 f = c.h_scalars[S_BIGGRP];
         const u32 limit = !(f & 1) ? kLocalCountLimit : !(f & 2) ? 512u : kPoMaxGroup;
         const u32 C = (u32)kPoCap - limit;
-        // groups sorted by the position of their head suffix (stable: members stay in slot order)
-        u32 *head_pos = a_slot1, *head_slot = a_slot1 + G;
-        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * 8 + (double)G * 8, po_heads_kernel, (u32)ceil_div(N, 256), 256, 0, a_pos, a_grp, slot_cur, N, head_pos, head_slot);
-        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * (8 + 12), po_keys_kernel, (u32)ceil_div(N, 256), 256, 0, a_pos, a_grp, head_pos, head_slot, N, keyA, valA);
+        // groups sorted by the position of their head suffix; members keep their slot order (po_rounds.cuh)
+        u32 *ghead_pos = (u32 *)keyA, *gid = ghead_pos + G, *ghead_slot = gid + G;            // 3 G     <= 1.5 n words of keyA's 2 n
+        u32 *tmpk = (u32 *)keyB, *tmpv = tmpk + G, *gstart = tmpv + G;                        // 3 G + 1 <= 1.5 n + 1 words of keyB's 2 n
+        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * 4 + (double)G * 24, po_group_table_kernel, (u32)ceil_div(N, 256), 256, 0,
+                   a_pos, a_grp, slot_cur, N, gstart, ghead_pos, ghead_slot, gid);
         const int pos_bits = bits_for(n - 1);
-        int drop = pos_bits > 24 ? pos_bits - 24 : 0;                 // 3 digit passes: groups whose heads share the dropped low bits stay in slot order
-        { const char *env = getenv("LIBSAIS_CUDA_PO_DROP"); if (env && *env) { drop = atoi(env); if (drop < 0) drop = 0; if (drop >= pos_bits) drop = pos_bits - 1; } }
         int bin_shift = 7;
         { const char *env = getenv("LIBSAIS_CUDA_PO_BIN"); if (env && *env) { bin_shift = atoi(env); if (bin_shift < 0) bin_shift = 0; if (bin_shift > 24) bin_shift = 24; } }
-        RoundStat r0; r0.h = h; r0.n_active = N; r0.n_groups = G; r0.passes = 0; r0.key_bits = pos_bits - drop;
-        where = RadixSort<u64, u32>::sort(c, keyA, valA, keyB, valB, N, 32 + drop, 32 + pos_bits, sort_temp, err, &r0.passes);
+        RoundStat r0; r0.h = h; r0.n_active = N; r0.n_groups = G; r0.passes = 0; r0.key_bits = pos_bits;
+        c.pass_class_override = KC_ROUND_KEYS;
+        where = RadixSort<u32, u32>::sort(c, ghead_pos, gid, tmpk, tmpv, G, 0, pos_bits, sort_temp, err, &r0.passes);
+        c.pass_class_override = -1;
         if (where < 0) return -2;
-        const u64 *kv_k = where ? keyB : keyA; const u32 *kv_v = where ? valB : valA;
-        u32 *pair = (u32 *)(where ? keyA : keyB);
-        u32 *lp[2] = {a_pos, a_slot0}, *lr[2] = {a_grp, a_slot1};
+        const u32 *sg = where ? tmpv : gid;                  // group ids by ascending head position
+        u32 *newstart = where ? ghead_pos : tmpk;            // the sort's other key buffer is free
+        {
+            const u64 nb = ceil_div(G, (u64)kPoScanChunk);
+            u32 *bsum = (u32 *)sort_temp;
+            LSC_LAUNCH(c, KC_ROUND_KEYS, (double)G * 12, po_scan_sums_kernel, (u32)nb, kPoScanThreads, 0, sg, gstart, G, bsum);
+            LSC_LAUNCH(c, KC_ROUND_KEYS, (double)nb * 8, po_scan_top_kernel, 1, 1024, 0, bsum, nb);
+            LSC_LAUNCH(c, KC_ROUND_KEYS, (double)G * 16, po_scan_apply_kernel, (u32)nb, kPoScanThreads, 0, sg, gstart, G, bsum, newstart);
+        }
+        LSC_LAUNCH(c, KC_ROUND_KEYS, (double)N * 16 + (double)G * 12, po_move_kernel, (u32)ceil_div(N, 256), 256, 0,
+                   a_pos, a_grp, N, gstart, newstart, ghead_slot, valA, valB);
+        u32 *lp[2] = {a_pos, valA}, *lr[2] = {a_grp, valB};    // lists: out = [cur], in = [cur ^ 1]
+        u32 *pair_pos = a_slot0, *pair_rank = a_slot1;
         int cur = 0; bool first = true;
         while (N > 0) {
             if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
@@ -1061,14 +1087,14 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             c.check(cudaMemsetAsync(sort_temp, 0, tiles * sizeof(u64), st));
             c.check(cudaMemsetAsync(c.d_scalars + S_TICKET, 0, sizeof(u64), st));
             c.check(cudaMemsetAsync(c.d_scalars + S_NACT, 0, 2 * sizeof(u64), st));
-            PoArgs pa; pa.kv_keys = kv_k; pa.kv_vals = kv_v; pa.a_pos = lp[cur ^ 1]; pa.a_rank = lr[cur ^ 1];
+            PoArgs pa; pa.kv_keys = nullptr; pa.kv_vals = nullptr; pa.a_pos = lp[cur ^ 1]; pa.a_rank = lr[cur ^ 1];
             pa.N = N; pa.n = n; pa.h = h; pa.C = C; pa.bin_shift = bin_shift; pa.ISA = ISA; pa.o_pos = lp[cur]; pa.o_rank = lr[cur];
-            pa.pair_pos = pair; pa.pair_rank = where ? valA : valB;                  // both 16-byte aligned (po_apply_kernel)
+            pa.pair_pos = pair_pos; pa.pair_rank = pair_rank;                        // both 16-byte aligned (po_apply_kernel)
             pa.SA = SA; pa.rows = bwt_mode ? opt.bwt_rows : nullptr; pa.text = bwt_mode ? (const u8 *)d_T : nullptr;
             pa.aux_mask = ra.aux_mask; pa.aux_shift = ra.aux_shift; pa.aux_I = opt.aux_I; pa.primary = c.d_scalars + S_PRIMARY;
             pa.status = (u64 *)sort_temp; pa.ticket = (u32 *)(c.d_scalars + S_TICKET); pa.out_counts = c.d_scalars + S_NACT; pa.err = err;
-            if (first) LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (12 + 4 + 8 + 8), po_round_kernel<true>, (u32)tiles, kPoThreads, 0, pa);
-            else       LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (8 + 4 + 8 + 8), po_round_kernel<false>, (u32)tiles, kPoThreads, 0, pa);
+            pa.ntiles = (u32)tiles;
+            LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (8 + 4 + 8 + 8), po_round_kernel<false>, (u32)tiles, kPoThreads, 0, pa);
             LSC_LAUNCH(c, KC_SCATTER, (double)N * 12, po_apply_kernel, (u32)ceil_div(N, 2048), 256, 0, pa.pair_pos, pa.pair_rank, N, ISA);
             if (!read_round_scalars(c)) return -2;
             N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];

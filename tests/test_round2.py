@@ -237,7 +237,7 @@ def test_position_ordered_rounds(cu):
     """Rounds >= 1 on the position-ordered active list (po_rounds.cuh) against the slot-ordered rounds of round 1
     and the oracle: mutated copies (groups of `copies` suffixes that take many rounds), exact repeats (ties that
     only the end of the text breaks), runs, texts whose groups straddle the 128 / 512 / 1024 limits, small lists
-    (LIBSAIS_CUDA_LOCAL_MIN lowers the threshold so short texts take the path), every key-drop of the group sort.
+    (LIBSAIS_CUDA_LOCAL_MIN lowers the threshold so short texts take the path), several update-bin widths.
     SA, BWT + primary index and the aux samples must be bit-exact."""
     o = _best_cpu()
     rng = np.random.default_rng(2024)
@@ -249,7 +249,7 @@ def test_position_ordered_rounds(cu):
              "small": gen.repetitive_dna(300, 20), "binary": (rng.integers(0, 2, 300_000) + 48).astype(np.uint8)}
     texts["mutated_bytes"] = texts["bytes_copies"].copy()
     texts["mutated_bytes"][rng.integers(0, len(texts["mutated_bytes"]), 300)] = 7
-    knobs = ("LIBSAIS_CUDA_PO", "LIBSAIS_CUDA_LOCAL_MIN", "LIBSAIS_CUDA_PO_DROP")
+    knobs = ("LIBSAIS_CUDA_PO", "LIBSAIS_CUDA_LOCAL_MIN", "LIBSAIS_CUDA_PO_BIN")
     try:
         for name, T in texts.items():
             rs, SAr = o.sa(T)
@@ -260,7 +260,7 @@ def test_position_ordered_rounds(cu):
                     os.environ.pop(k, None)
                 os.environ["LIBSAIS_CUDA_PO"] = po; os.environ["LIBSAIS_CUDA_LOCAL_MIN"] = lmin
                 if drop is not None:
-                    os.environ["LIBSAIS_CUDA_PO_DROP"] = drop
+                    os.environ["LIBSAIS_CUDA_PO_BIN"] = drop
                 rc, SA = cu.sa(T)
                 assert rc == 0 and (SA == SAr).all(), (name, po, lmin, drop)
                 rcb, U = cu.bwt(T)

@@ -40,6 +40,10 @@ if hi:
     for i, r in enumerate(data):
         reg[i // 50] += int(r[si])
     print("by 50-instr region:", {k * 50: round(100 * v / tot, 1) for k, v in sorted(reg.items())})
+    regi = collections.Counter()
+    for i, r in enumerate(data):
+        regi[i // 50] += int(r[ie])
+    print("warp-instructions executed by 50-instr region (%):", {k * 50: round(100 * v / max(toti, 1), 1) for k, v in sorted(regi.items())})
 # per CUDA source line (needs -lineinfo and --import-source on)
 cu = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(cu)))
