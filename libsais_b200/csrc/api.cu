@@ -82,6 +82,7 @@ struct Call {
     ~Call() {
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
+        if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);       // nothing of this call may still be writing the caller's buffers
         if (c.failed()) { cudaStreamSynchronize(c.stream); cudaGetLastError(); }
     }
 };
@@ -292,11 +293,30 @@ IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *f
     call.start_timer();
     SAResult res; SAOptions opt;
     opt.want_sa = false; opt.bwt_rows = d_rows; opt.aux_r = aux ? (u64)r : 0; opt.aux_I = d_I;
+    // A pinned output buffer receives the rows of settled slots while round 0 still sorts (boundary
+    // src/libsais.c:7097-7121): the device alias of U is needed for the few rows that are sent again at the end.
+    u8 *U_dev_alias = nullptr;
+    if (host_is_pinned(U) && cudaHostGetDevicePointer((void **)&U_dev_alias, (void *)U, 0) == cudaSuccess && U_dev_alias) { opt.h_U = U; opt.h_T = T; }
+    else cudaGetLastError();
     if (build_sa(*c, d_T, 1, (u64)n, opt, &res) != 0) return -2;
     if (res.primary < 1 || res.primary > (u64)n) return -2;
-    if (run_bwt_finish(*c, d_T, d_rows, d_U, (u64)n, res.primary) != 0) return -2;
-    call.stop_timer();
-    if (!copy_d2h(*c, U, d_U, (size_t)n)) return -2;
+    const u64 p0 = res.primary - 1;
+    if (res.u_streamed && p0 >= res.p0_lo && p0 < res.p0_hi) {
+        // everything outside the bucket of suffix 0 is on its way; wait for those copies, then the bucket itself (two
+        // pieces around the dropped row) and the rows that were settled after round 0
+        c->check(cudaEventRecord(c->chunk_ev[Ctx::kChunkEvents - 1], c->copy_stream));
+        c->check(cudaStreamWaitEvent(c->stream, c->chunk_ev[Ctx::kChunkEvents - 1], 0));
+        if (p0 > res.p0_lo) c->check(cudaMemcpyAsync(U + res.p0_lo + 1, d_rows + res.p0_lo, p0 - res.p0_lo, cudaMemcpyDeviceToHost, c->stream));
+        if (p0 + 1 < res.p0_hi) c->check(cudaMemcpyAsync(U + p0 + 1, d_rows + p0 + 1, res.p0_hi - p0 - 1, cudaMemcpyDeviceToHost, c->stream));
+        if (run_bwt_patch(*c, res.patch_slots, res.n_patch, d_rows, U_dev_alias, p0) != 0) return -2;
+        call.stop_timer();
+        U[0] = T[n - 1];
+    } else {
+        if (opt.h_U && c->copy_stream) c->check(cudaStreamSynchronize(c->copy_stream));       // chunks may be in flight into U: let them land first
+        if (run_bwt_finish(*c, d_T, d_rows, d_U, (u64)n, res.primary) != 0) return -2;
+        call.stop_timer();
+        if (!copy_d2h(*c, U, d_U, (size_t)n)) return -2;
+    }
     if (n_aux && !download_indexes<IDX>(*c, d_I, I, n_aux, res.scratch)) return -2;
     if (!call.finish()) return -2;
     store_freq(*c, freq);

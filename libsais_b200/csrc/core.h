@@ -26,6 +26,10 @@ struct SAOptions {
     bool want_sa = true;          // materialise SA (false: BWT-only callers never need it)
     u32 *sa_out = nullptr;        // caller's device buffer for SA instead of an arena array
     u8 *bwt_rows = nullptr;       // byte texts only: rows[slot] = byte preceding the suffix in that SA slot
+    // BWT callers whose output buffer is pinned host memory: the rows of the slots that round 0 settles are copied to
+    // the host chunk by chunk while the remaining buckets are still being sorted (MSD path)
+    u8 *h_U = nullptr;            // host address of the caller's U
+    const u8 *h_T = nullptr;      // host address of the caller's T (its first symbols locate the row of suffix 0)
     u64 aux_r = 0;                // aux sampling: aux_I[p / r] = slot(p) + 1 for p % r == 0 (r a power of two)
     u32 *aux_I = nullptr;
 };
@@ -35,6 +39,11 @@ struct SAResult {
     u32 *ISA = nullptr;   // [n]   inverse suffix array; complete only when isa_complete
     bool isa_complete = false;
     u64 primary = 0;      // slot of suffix 0, plus 1 (= the BWT primary index)
+    // streamed rows (SAOptions::h_U): every slot outside [p0_lo, p0_hi) is already in the host buffer, shifted around the
+    // dropped row; the slots of patch_slots[0..n_patch) were unresolved after round 0 and must be sent again
+    bool u_streamed = false;
+    u64 p0_lo = 0, p0_hi = 0;
+    const u32 *patch_slots = nullptr; u64 n_patch = 0;
     void *scratch = nullptr;      // dead sort buffer, reusable by the caller after the build
     size_t scratch_bytes = 0;     // = 8n
 };
@@ -50,6 +59,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
 // Post-processing stages (all device pointers).
 //   bwt:   U[n] from the per-slot rows produced by build_sa (SAOptions::bwt_rows) and the primary index
 int run_bwt_finish(Ctx &c, const u8 *d_T, const u8 *d_rows, u8 *d_U, u64 n, u64 primary);
+//   streamed rows: rows of the slots listed in d_slots -> the caller's pinned U (device alias), shifted around the dropped row p0
+int run_bwt_patch(Ctx &c, const u32 *d_slots, u64 count, const u8 *d_rows, u8 *U_host_dev, u64 p0);
 //   plcp:  PLCP[n] from T (sym_bytes 1 or 4), SA.  d_T must be readable up to 16 bytes past the end.
 size_t plcp_workspace_bytes(u64 n);
 int run_plcp(Ctx &c, const void *d_T, int sym_bytes, const u32 *d_SA, u32 *d_PLCP, u64 n);

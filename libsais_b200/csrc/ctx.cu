@@ -28,6 +28,8 @@ void Ctx::destroy()
     for (auto e : event_pool) cudaEventDestroy(e);
     event_pool.clear();
     free_staging();
+    for (int i = 0; i < kChunkEvents; ++i) if (chunk_ev[i]) { cudaEventDestroy(chunk_ev[i]); chunk_ev[i] = nullptr; }
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
     if (dist_words) { cudaFree(dist_words); dist_words = nullptr; }
     if (ws) cudaFree(ws);
     if (d_scalars) cudaFree(d_scalars);
@@ -35,6 +37,15 @@ void Ctx::destroy()
     if (stream) cudaStreamDestroy(stream);
     ws = nullptr; d_scalars = nullptr; h_scalars = nullptr; stream = nullptr; ok = false;
     cudaGetLastError();
+}
+
+bool Ctx::ensure_copy_stream()
+{
+    if (copy_stream) return true;
+    if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); copy_stream = nullptr; return false; }
+    for (int i = 0; i < kChunkEvents; ++i)
+        if (cudaEventCreateWithFlags(&chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
 }
 
 bool Ctx::reserve(size_t bytes)

@@ -50,6 +50,12 @@ struct Ctx {
     // distributed building blocks: packed text kept across calls (sa_core.cu dist_prepare)
     u64 *dist_words = nullptr; u64 dist_n = 0; int dist_b = 0, dist_k = 0;
 
+    // second stream + events for results that leave while the call still computes (streamed BWT rows: sa_core.cu, api.cu)
+    cudaStream_t copy_stream = nullptr;
+    static const int kChunkEvents = 16;
+    cudaEvent_t chunk_ev[kChunkEvents] = {nullptr};
+    bool ensure_copy_stream();
+
     // pinned staging lanes for large pageable host transfers (hostcopy.cu)
     struct StageLane { cudaStream_t stream = nullptr; void *buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; };
     std::vector<StageLane> stage;

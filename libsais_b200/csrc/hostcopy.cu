@@ -104,6 +104,8 @@ static void lane_d2h(Ctx::StageLane *l, int device, char *h, const char *d, size
     }
 }
 
+bool host_is_pinned(const void *p) { return is_pinned(p); }
+
 bool copy_h2d(Ctx &c, void *d_dst, const void *h_src, size_t bytes)
 {
     if (bytes == 0) return true;

@@ -15,5 +15,7 @@ namespace lsc {
 // They return false on a CUDA failure (recorded in the context).
 bool copy_h2d(Ctx &c, void *d_dst, const void *h_src, size_t bytes);
 bool copy_d2h(Ctx &c, void *h_dst, const void *d_src, size_t bytes);
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory?
+bool host_is_pinned(const void *p);
 
 }  // namespace lsc

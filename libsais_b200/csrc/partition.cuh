@@ -987,12 +987,12 @@ static __global__ void __launch_bounds__(kBucketThreads, 2)
 bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, const uint4 *__restrict__ tb,
                    u64 n, u32 C, int key_shift, int R,             // R = K - 16: k-mer bits below the bucket prefix
                    u64 *__restrict__ kout, u32 *__restrict__ vout, u32 *err, const BucketFuse fz,
-                   const u32 *__restrict__ boff)
+                   const u32 *__restrict__ boff, const u32 tile0)       // tile0: first tile of this launch (the tiles may be launched in chunks)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BucketSmem &sm = *reinterpret_cast<BucketSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint4 ti = tb[2 * blockIdx.x], tn = tb[2 * blockIdx.x + 1];
+    const uint4 ti = tb[2 * (u64)(blockIdx.x + tile0)], tn = tb[2 * (u64)(blockIdx.x + tile0) + 1];
     const u64 s = ti.x;
     const u32 cnt = ti.y, B0 = ti.z, nb = ti.w;
     if (cnt == 0) return;

@@ -36,6 +36,24 @@ bwt_finish_kernel(const u8 *__restrict__ T, const u8 *__restrict__ rows, u8 *__r
         U[o] = o == 0 ? T[n - 1] : rows[o <= p0 ? o - 1 : o];
 }
 
+// Streamed rows (sa_core.cu): the rows of the slots round 0 settled are already in the caller's pinned buffer.  The slots
+// that were still open then (a few thousand on random text) are final now: their bytes go straight into the host buffer
+// (zero-copy stores through the buffer's device alias), shifted around the dropped row p0.
+__global__ void __launch_bounds__(256)
+bwt_patch_kernel(const u32 *__restrict__ slots, u64 count, const u8 *__restrict__ rows, u8 *__restrict__ U_host, u64 p0)
+{
+    const u64 j = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (j >= count) return;
+    const u64 s = slots[j];
+    if (s != p0) U_host[s + (s < p0 ? 1 : 0)] = rows[s];
+}
+
+int run_bwt_patch(Ctx &c, const u32 *d_slots, u64 count, const u8 *d_rows, u8 *U_host_dev, u64 p0)
+{
+    if (count) LSC_LAUNCH(c, KC_BWT, (double)count * 6, bwt_patch_kernel, (u32)ceil_div(count, 256), 256, 0, d_slots, count, d_rows, U_host_dev, p0);
+    return c.failed() ? -2 : 0;
+}
+
 int run_bwt_finish(Ctx &c, const u8 *d_T, const u8 *d_rows, u8 *d_U, u64 n, u64 primary)
 {
     LSC_LAUNCH(c, KC_BWT, (double)n * 2, bwt_finish_kernel, (u32)ceil_div(ceil_div(n, 16), 256), 256, 0, d_T, d_rows, d_U, n, primary - 1);

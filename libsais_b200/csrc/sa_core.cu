@@ -755,13 +755,14 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     // ---- alphabet: bits per symbol, order-preserving code map (bytes), key width
     int b = 8; double entropy = 8.0;
     u8 *d_lut = nullptr;
+    u8 lut[256];
     bool lut_identity = false;
     if (sym_bytes == 1) {
         run_byte_histogram(c, (const u8 *)d_T, n);
         c.check(cudaMemcpyAsync(c.h_scalars + S_FREQ, c.d_scalars + S_FREQ, 256 * sizeof(u64),
                                 cudaMemcpyDeviceToHost, st));
         if (!c.sync()) return -2;
-        u8 lut[256]; int sigma = 0; entropy = 0;
+        int sigma = 0; entropy = 0;
         for (int s = 0; s < 256; ++s) {
             u64 f = c.h_scalars[S_FREQ + s];
             lut[s] = (u8)(sigma ? sigma : 0);
@@ -830,7 +831,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     // ---- MSD path (partition.cuh): when the 16-bit key prefixes spread the suffixes over small buckets (random
     // bytes, iid DNA: any near-uniform source), two UNSTABLE partition passes on the top 16 key bits and an
     // in-shared-memory finish of every bucket replace the K/8 stable LSD passes.  Same sorted arrays.
-    bool msd = false, msd_fused = false;
+    bool msd = false, msd_fused = false, stream_rows = false;
     u32 *m_boff = nullptr, *m_tstart = nullptr, *m_H = nullptr; u64 *m_base = nullptr; u64 m_maxb = 0, m_maxnt = 0;
     // LIBSAIS_CUDA_PART_PIPE: bit 0 = persistent double-buffered kernel for the first MSD level, bit 1 = for the second.
     // Measured on B200 (profiles/part_pass_r2.md): it pays for the array source (TMA prefetch: 2.15 -> 1.99 ms) and not for the
@@ -875,6 +876,13 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
                                LSC_LAUNCH(c, KC_SORT_HIST, hb, hist16_kernel<1>, grid, kHist16Threads, hsm, words, n, h16, m_H, nunits, upc, ut, tpc, ptile, flag); }
             LSC_LAUNCH(c, KC_SORT_SCAN, 65536.0 * 8, scan16_kernel, 1, 1024, 0, h16, m_boff, m_base, m_tstart, m_H, nseg1, c.d_scalars + S_MSD, ptile);
             c.check(cudaMemcpyAsync(c.h_scalars + S_MSD, c.d_scalars + S_MSD, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            if (opt.h_U && opt.h_T && bwt_mode) {
+                // bucket of suffix 0 (the row the BWT drops) from the first 16 / b symbols of the text: its slot range
+                // [p0_lo, p0_hi) tells, before the sort, on which side of the dropped row every other slot lies
+                u32 pre = 0;
+                for (int i = 0; i < 16 / b; ++i) pre = (pre << b) | ((u64)i < n ? (u32)lut[opt.h_T[i]] : 0u);
+                c.check(cudaMemcpyAsync(c.h_scalars + S_MSD + 3, m_boff + pre, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            }
             if (!c.sync()) return -2;
             m_maxb = c.h_scalars[S_MSD]; m_maxnt = c.h_scalars[S_MSD + 1];
             msd = c.h_scalars[S_MSD + 2] == 0 && m_maxb <= (u64)kBucketMaxBucket;
@@ -921,14 +929,36 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         {
             const double ab = (double)n * ((k32 ? 8.0 : 12.0) + (msd_fused ? 4.0 + (bwt_mode ? 1.0 : 0.0) + 0.25 : 12.0));
             u32 *vout = (msd_fused && SA) ? SA : valA;
+            // Streamed rows: the tiles are launched in chunks; when a chunk is done every slot below its last window is final
+            // for round 0 and its row bytes start their way to the caller's pinned buffer on the copy stream, shifted by one
+            // below the dropped row.  The bucket of suffix 0 itself waits for the primary index (api.cu bwt_body).
+            const u32 *h_b0 = (const u32 *)(c.h_scalars + S_MSD + 3);
+            const u64 p0_lo = h_b0[0], p0_hi = h_b0[1];
+            stream_rows = msd_fused && bwt_mode && opt.h_U && opt.h_T && btiles >= 64 && p0_lo < p0_hi && p0_hi <= n && c.ensure_copy_stream();
+            { const char *env = getenv("LIBSAIS_CUDA_STREAM_ROWS"); if (env && *env && atoi(env) == 0) stream_rows = false; }
+            const int nchunk = stream_rows ? 8 : 1;
+            out->p0_lo = p0_lo; out->p0_hi = p0_hi;
 #define LSC_BUCKET_SORT(IN32, FUSED)                                                                                                        \
             do {                                                                                                                            \
                 c.check(cudaFuncSetAttribute(bucket_sort_kernel<IN32, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem))); \
-                LSC_LAUNCH(c, KC_BUCKET_SORT, ab, (bucket_sort_kernel<IN32, FUSED>), (u32)btiles, kBucketThreads, sizeof(BucketSmem),       \
-                           keyB, valB, tb, n, Cw, key_shift, K - 16, keyA, vout, err, fz, m_boff);                                          \
+                LSC_LAUNCH(c, KC_BUCKET_SORT, ab * (double)(t1 - t0) / (double)btiles, (bucket_sort_kernel<IN32, FUSED>), (u32)(t1 - t0), kBucketThreads, sizeof(BucketSmem), \
+                           keyB, valB, tb, n, Cw, key_shift, K - 16, keyA, vout, err, fz, m_boff, (u32)t0);                                 \
             } while (0)
-            if (k32) { if (msd_fused) LSC_BUCKET_SORT(true, true); else LSC_BUCKET_SORT(true, false); }
-            else     { if (msd_fused) LSC_BUCKET_SORT(false, true); else LSC_BUCKET_SORT(false, false); }
+            for (int ck = 0; ck < nchunk; ++ck) {
+                const u64 t0 = btiles * (u64)ck / nchunk, t1 = btiles * (u64)(ck + 1) / nchunk;
+                if (t1 == t0) continue;
+                if (k32) { if (msd_fused) LSC_BUCKET_SORT(true, true); else LSC_BUCKET_SORT(true, false); }
+                else     { if (msd_fused) LSC_BUCKET_SORT(false, true); else LSC_BUCKET_SORT(false, false); }
+                if (stream_rows) {
+                    c.check(cudaEventRecord(c.chunk_ev[ck], st));
+                    c.check(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[ck], 0));
+                    const u64 lo = t0 * (u64)Cw, hi = ck == nchunk - 1 ? n : t1 * (u64)Cw;      // slots that are final now
+                    const u64 a1 = hi < p0_lo ? hi : p0_lo;                                      // [lo, a1): below the dropped row -> U[slot + 1]
+                    if (lo < a1) c.check(cudaMemcpyAsync(opt.h_U + lo + 1, opt.bwt_rows + lo, a1 - lo, cudaMemcpyDeviceToHost, c.copy_stream));
+                    const u64 b0s = lo > p0_hi ? lo : p0_hi;                                     // [b0s, hi): above it -> U[slot]
+                    if (b0s < hi) c.check(cudaMemcpyAsync(opt.h_U + b0s, opt.bwt_rows + b0s, hi - b0s, cudaMemcpyDeviceToHost, c.copy_stream));
+                }
+            }
 #undef LSC_BUCKET_SORT
         }
         rs.passes = 2;
@@ -992,6 +1022,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     bool lazy = N * 32 <= n;
     { const char *env = getenv("LIBSAIS_CUDA_LAZY_ISA"); if (env && *env) lazy = atoi(env) != 0; }
     u64 *rk0 = ks, *rk1 = ko; u32 *rv0 = vbuf, *rv1 = vo;
+    if (N == 0 && stream_rows) out->u_streamed = true;          // everything settled in round 0: nothing to send again
     if (N > 0) {
         if (lazy) {
             rk0 = c.alloc_n<u64>(N); rk1 = c.alloc_n<u64>(N); rv0 = c.alloc_n<u32>(N); rv1 = c.alloc_n<u32>(N);
@@ -1002,6 +1033,14 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         if (lazy) {
             ra.isa_all = 0;
             LSC_LAUNCH(c, KC_RANK_INIT, (double)N * 16, rank_apply_kernel<true>, (u32)ceil_div(rank_tiles, kApplyTiles), kRankThreads, 0, ra);
+            if (stream_rows && N <= ((u64)1 << 20)) {
+                // streamed rows: the slots that are still open keep the list of rows to send again when they are final
+                u32 *saved = c.alloc_n<u32>(N);
+                if (saved) {
+                    c.check(cudaMemcpyAsync(saved, slot_cur, N * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+                    out->patch_slots = saved; out->n_patch = N; out->u_streamed = true;
+                } else c.last_error = cudaSuccess;
+            }
         } else {
             // every rank is needed: (position, rank) pairs in slot order, then a locality-partitioned scatter
             ra.isa_all = 1; ra.pair_idx = (u32 *)ko; ra.pair_val = (u32 *)ko + n;

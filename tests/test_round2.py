@@ -270,3 +270,42 @@ def test_position_ordered_rounds(cu):
     finally:
         for k in knobs:
             os.environ.pop(k, None)
+
+
+def test_bwt_streamed_rows_into_pinned_buffers(cu):
+    """libsais_bwt / libsais_bwt_aux with PINNED caller buffers: the rows of the slots that round 0 settles leave for the
+    host while the remaining buckets are sorted, the bucket of suffix 0 and the late rows follow (api.cu bwt_body,
+    sa_core.cu streamed rows).  Same bytes and primary index as the oracle -- for texts whose suffix 0 is settled in
+    round 0, texts where it is not (a prefix that occurs twice), texts that fall back to the one-piece copy (everything
+    repeated), and with the streaming switched off."""
+    import torch
+    import libsais_b200
+    lib = libsais_b200.load_library()
+    o = _best_cpu()
+    rng = np.random.default_rng(5)
+    R = gen.rand_bytes(11, 3_000_000)
+    twice = R.copy(); twice[1_500_000:1_500_040] = twice[:40]                 # suffix 0 shares 40 bytes with suffix 1.5e6
+    texts = {"bytes_3M": R, "dna_6M": gen.dna(12, 6_000_000), "prefix_twice": twice,
+             "sigma16": (rng.integers(0, 16, 2_000_000) + 65).astype(np.uint8), "all_repeated": np.tile(gen.rand_bytes(13, 700_000), 2),
+             "zero_head": np.concatenate([np.zeros(5, dtype=np.uint8), gen.rand_bytes(14, 1_000_000)])}
+    lib.libsais_bwt.restype = C.c_int32
+    lib.libsais_bwt_aux.restype = C.c_int32
+    try:
+        for name, T in texts.items():
+            n = len(T)
+            rb, Ur = o.bwt(T)
+            Ir = o.bwt_aux(T, 256)[2]
+            for stream in ("1", "0"):
+                os.environ["LIBSAIS_CUDA_STREAM_ROWS"] = stream
+                Tp = torch.from_numpy(T).pin_memory()
+                Up = torch.full((n,), 0xEE, dtype=torch.uint8).pin_memory()
+                Ap = torch.empty(n, dtype=torch.int32).pin_memory()
+                rc = lib.libsais_bwt(C.c_void_p(Tp.data_ptr()), C.c_void_p(Up.data_ptr()), C.c_void_p(Ap.data_ptr()), C.c_int32(n), C.c_int32(0), None)
+                assert rc == rb and (Up.numpy() == Ur).all(), (name, stream, rc, rb)
+                Up.fill_(0xEE)
+                Ip = torch.zeros((n - 1) // 256 + 1, dtype=torch.int32).pin_memory()
+                rc = lib.libsais_bwt_aux(C.c_void_p(Tp.data_ptr()), C.c_void_p(Up.data_ptr()), C.c_void_p(Ap.data_ptr()), C.c_int32(n), C.c_int32(0), None,
+                                         C.c_int32(256), C.c_void_p(Ip.data_ptr()))
+                assert rc == 0 and (Up.numpy() == Ur).all() and (Ip.numpy() == Ir).all(), (name, stream)
+    finally:
+        os.environ.pop("LIBSAIS_CUDA_STREAM_ROWS", None)
