@@ -94,6 +94,30 @@ __device__ __forceinline__ void po_cnt_lt(float &c, u32 x, u32 r)
 
 static const int kPoItems = kPoCap / kPoIPT + kPoCap / 2;   // work items of the ordering step: <= cnt/8 + (groups <= cnt/2)
 
+// the same with two maxima (latest group head, latest run head)
+__device__ __forceinline__ void po_block_scan3(u32 max1, u32 max2, u32 mysum, u32 &ex1, u32 &ex2, u32 &exsum, u32 &total, u32 (*s_scan)[kPoWarps], int lane, int warp)
+{
+    u32 m1 = max1, m2 = max2, s = mysum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const u32 o1 = __shfl_up_sync(0xffffffffu, m1, off), o2 = __shfl_up_sync(0xffffffffu, m2, off), os = __shfl_up_sync(0xffffffffu, s, off);
+        if (lane >= off) { m1 = o1 > m1 ? o1 : m1; m2 = o2 > m2 ? o2 : m2; s += os; }
+    }
+    if (lane == 31) { s_scan[0][warp] = m1; s_scan[1][warp] = s; s_scan[2][warp] = m2; }
+    u32 e1 = __shfl_up_sync(0xffffffffu, m1, 1), e2 = __shfl_up_sync(0xffffffffu, m2, 1), es = __shfl_up_sync(0xffffffffu, s, 1);
+    if (lane == 0) { e1 = 0; e2 = 0; es = 0; }
+    __syncthreads();
+    u32 c1 = 0, c2 = 0, cs = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kPoWarps; ++w) {
+        const u32 x = s_scan[0][w], y = s_scan[1][w], z = s_scan[2][w];
+        if (w < warp) { c1 = x > c1 ? x : c1; c2 = z > c2 ? z : c2; cs += y; }
+        tot += y;
+    }
+    ex1 = e1 > c1 ? e1 : c1; ex2 = e2 > c2 ? e2 : c2; exsum = es + cs; total = tot;
+    __syncthreads();
+}
+
 template <bool KV>
 __global__ void __launch_bounds__(kPoThreads, 4)
 po_round_kernel(const PoArgs a)
@@ -106,7 +130,7 @@ po_round_kernel(const PoArgs a)
     __shared__ __align__(16) unsigned short s_src[kPoCap];  // sorted index -> list index
     __shared__ __align__(16) unsigned short s_item[kPoItems];   // work item -> first list index of its (up to) 8 elements; later s_bin
     __shared__ __align__(16) u32 s_out[kPoCap];  // rank updates of the tile, staged in bin order (positions reuse s_rk)
-    __shared__ u32 s_scan[2][kPoWarps];
+    __shared__ u32 s_scan[3][kPoWarps];
     __shared__ u32 bounds[2];
     __shared__ u32 s_tile;
     __shared__ u64 s_base;
@@ -168,33 +192,74 @@ po_round_kernel(const PoArgs a)
         __syncthreads();
         const u32 idx0 = (u32)tid * kPoIPT;
         const int nv = idx0 < cnt ? (cnt - idx0 < (u32)kPoIPT ? (int)(cnt - idx0) : kPoIPT) : 0;
-        // ---- group starts and ends (blocked: a thread owns 8 consecutive elements)
+        // ---- group starts and ends, and RUNS: maximal stretches of neighbours of one group with the same gathered rank.
+        // Only the head of a run has to be ordered by counting; the sorted index of a follower is its head's plus the
+        // distance (equal keys keep their list order).  The groups of a repetitive text split off a few members per round,
+        // so most of their elements are followers.  (blocked: a thread owns 8 consecutive elements)
+        unsigned short *s_rs = reinterpret_cast<unsigned short *>(s_out);      // head of the element's run   } s_out is idle
+        unsigned short *s_dh = s_rs + kPoCap;                                  // sorted index of a run head  } until the emit step
         u32 hm = 0;                              // which of my elements head a group
+        u32 nrun = 0;                            // runs of the tile
         {
-            u32 rk[kPoIPT];
+            u32 rk[kPoIPT], rr[kPoIPT];
 #pragma unroll
-            for (int i = 0; i < kPoIPT; ++i) rk[i] = i < nv ? s_rk[idx0 + i] : 0;
-            const u32 rprev = (nv && idx0 > 0) ? s_rk[idx0 - 1] : 0;
-            u32 last = 0;
+            for (int i = 0; i < kPoIPT; ++i) { rk[i] = i < nv ? s_rk[idx0 + i] : 0; rr[i] = i < nv ? s_r[idx0 + i] : 0; }
+            const u32 rprev = (nv && idx0 > 0) ? s_rk[idx0 - 1] : 0, rrprev = (nv && idx0 > 0) ? s_r[idx0 - 1] : 0;
+            u32 last = 0, lastrun = 0, rm = 0;
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
                 const bool hd = i < nv && (idx0 + i == 0 || rk[i] != (i ? rk[i - 1] : rprev));
+                const bool rh = i < nv && (hd || rr[i] != (i ? rr[i - 1] : rrprev));
                 if (hd) { hm |= 1u << i; last = idx0 + i; }
+                if (rh) { rm |= 1u << i; lastrun = idx0 + i; }
             }
-            u32 carry, dummy, dummy2;
-            po_block_scan(last, 0, carry, dummy, dummy2, s_scan, lane, warp);
-            u32 cur = carry;
+            u32 carry, carryrun, before;
+            po_block_scan3(last, lastrun, (u32)__popc(rm), carry, carryrun, before, nrun, s_scan, lane, warp);
+            u32 cur = carry, currun = carryrun;
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
                 if (i < nv) {
                     const u32 idx = idx0 + i;
                     if ((hm >> i) & 1u) { if (idx > 0) s_ge[cur] = (unsigned short)idx; cur = idx; }
+                    if ((rm >> i) & 1u) {
+                        currun = idx;
+                        const u32 k = before + (u32)__popc(rm & ((1u << i) - 1u));
+                        if (k < (u32)kPoItems) s_item[k] = (unsigned short)idx;         // list of the run heads (used when they are few)
+                    }
                     s_gs[idx] = (unsigned short)cur;
+                    s_rs[idx] = (unsigned short)currun;
                     if (idx == cnt - 1) s_ge[cur] = (unsigned short)cnt;
                 }
             }
         }
         __syncthreads();
+        if (nrun * 4 <= cnt) {
+            // ---- few runs: one thread per run head counts the members of its group in front of it (ties included) and
+            // behind it (smaller ranks only)
+            // (8 lanes share a run head and split its group between them: with one thread per head a few warps walked whole
+            // groups while the rest of the CTA waited at the barrier)
+            const u32 sub = (u32)lane & 7u;
+            for (u32 k0 = 0; k0 < nrun; k0 += kPoThreads / 8) {
+                const u32 k = k0 + ((u32)tid >> 3);
+                u32 c = 0, e = 0, g0 = 0;
+                if (k < nrun) {
+                    e = s_item[k]; g0 = s_gs[e];
+                    const u32 g1 = s_ge[g0], r = s_r[e];
+                    for (u32 j = g0 + sub; j < g1; j += 8) {
+                        const u32 x = s_r[j];
+                        c += (u32)((j < e) ? (x <= r) : (j > e && x < r));
+                    }
+                }
+                c += __shfl_xor_sync(0xffffffffu, c, 1); c += __shfl_xor_sync(0xffffffffu, c, 2); c += __shfl_xor_sync(0xffffffffu, c, 4);
+                if (k < nrun && sub == 0) s_dh[e] = (unsigned short)(g0 + c);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kPoIPT; ++i) {
+                const u32 e = i * kPoThreads + tid;
+                if (e < cnt) { const u32 h0 = s_rs[e]; s_src[(u32)s_dh[h0] + (e - h0)] = (unsigned short)e; }
+            }
+        } else {
         // ---- work items of the ordering step: a group of s elements is cut into ceil(s / 8) runs of consecutive
         // elements, one item each, so that the 8 elements of an item always share their group (a thread that owned 8
         // consecutive elements of the TILE would straddle groups and drag its whole warp through both of them)
@@ -245,6 +310,7 @@ po_round_kernel(const PoArgs a)
             }
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) if ((u32)i < ne) s_src[g0 + (u32)c[i]] = (unsigned short)(e0 + i);
+        }
         }
         __syncthreads();
         // ---- rank (blocked over the sorted order): sub-group heads, finals, new ranks, output offsets
