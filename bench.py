@@ -332,9 +332,11 @@ KERNEL_NAMES = {
     "sort_pass": "sort_pass_kernel<u64,u32> (stable onesweep digit pass)",
     "sort_pass_gen": "part_pass_kernel<KmerSrc> (first MSD level: keys built from the packed text, partition by the top 8 key bits)",
     "part_pass": "part_pass_kernel<ArraySrc,segmented> (second MSD level: unstable partition by key bits 8..15)",
-    "bucket_sort": "bucket_sort_kernel (16-bit buckets finished in shared memory)",
-    "rank_init": "rank_flags/rank_apply<round 0>", "local_sort": "local_count/local_sort kernels (rounds >= 1)",
-    "scatter": "partitioned scatter (ISA updates)", "rank_update": "rank_flags/rank_apply<rounds >= 1>",
+    "bucket_sort": "bucket_sort_kernel<k32,fused> (16-bit buckets finished in shared memory; emits positions, BWT rows, head/active flags)",
+    "rank_init": "rank_agg (MSD path) or rank_flags, rank_apply<round 0>",
+    "local_sort": "po_round_kernel (rounds >= 1 on the position-ordered list; slot-ordered fallback: local_count/local_sort)",
+    "round_keys": "group reorder of the position-ordered rounds (table, sort of the groups, scan, move) / round_keys",
+    "scatter": "po_apply_kernel (ISA updates of a round) / partitioned scatter (round-0 ranks, phi)", "rank_update": "rank_flags/rank_apply<rounds >= 1>",
 }
 
 
@@ -660,9 +662,9 @@ def main():
                    "rounds": rounds, "timed_region": "per-kernel CUDA events recorded inside it (profiling on)" if not args.no_profile else "profiling off"},
         "e2e": {"value": round(e2e, 1), "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": n + 4,
                 "ms_per_step": round(e2e_ms / args.steps, 3), "api": "libsais_bwt_ctx(host pinned T, U), one host thread",
-                "note": "H2D (whole text), kernels and D2H (whole BWT) of ONE call are serial by data dependence: every sort pass needs the global "
-                        "histogram of the whole text and the last BWT row is known only after the last round; overlap across calls is what "
-                        "libsais_cuda_bwt_batch does (see c4)"},
+                "note": "H2D of the whole text first (every sort pass needs the histogram of the whole text); the D2H overlaps the sort: the "
+                        "output buffer is pinned, so the rows of settled slots leave chunk by chunk while the remaining buckets are sorted, and "
+                        "the bucket of suffix 0 and the few rows settled after round 0 follow (sa_core.cu streamed rows; api.cu bwt_body)"},
         "gpu_launches": int(launches), "roofline": roof, "kernels": kern, "clocks": clocks,
     }
     if not args.no_cpu_baseline:

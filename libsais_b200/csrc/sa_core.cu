@@ -729,8 +729,13 @@ static int choose_key_symbols(u64 n, int b, double entropy_bits, int max_key_bit
     double kk = std::ceil(need / entropy_bits);
     int k = kk > (double)kmax ? kmax : (int)kk;
     if (k < 1) k = 1;
-    // round the key up to whole digit passes: extra symbols are free inside a pass
+    // round the key to whole digit passes: extra symbols are free inside a pass -- but a key that overshoots a pass
+    // boundary by a bit or two is cut back instead (the "+ 10" above is margin; a sixth LSD pass over 1.9e9 pairs is 16 ms)
     int passes = (k * b + kRadixBits - 1) / kRadixBits;
+    if (passes > 2 && k * b - (passes - 1) * kRadixBits <= 2 && ((passes - 1) * kRadixBits) / b >= 1) {
+        --passes;
+        return ((passes * kRadixBits) / b) < kmax ? (passes * kRadixBits) / b : kmax;
+    }
     int k2 = (passes * kRadixBits) / b;
     if (k2 > kmax) k2 = kmax;
     return k2 > k ? k2 : k;
@@ -927,7 +932,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         fz.aux_I = opt.aux_I; fz.aux_mask = opt.aux_I ? opt.aux_r - 1 : 0; fz.aux_shift = opt.aux_I ? bits_for(opt.aux_r) - 1 : 0;
         fz.primary = c.d_scalars + S_PRIMARY;
         {
-            const double ab = (double)n * ((k32 ? 8.0 : 12.0) + (msd_fused ? 4.0 + (bwt_mode ? 1.0 : 0.0) + 0.25 : 12.0));
+            const double ab = (double)n * ((k32 ? 8.0 : 12.0) + (msd_fused ? 4.0 + (bwt_mode ? 1.0 : 0.0) + 1.0 : 12.0));
             u32 *vout = (msd_fused && SA) ? SA : valA;
             // Streamed rows: the tiles are launched in chunks; when a chunk is done every slot below its last window is final
             // for round 0 and its row bytes start their way to the caller's pinned buffer on the copy stream, shifted by one
