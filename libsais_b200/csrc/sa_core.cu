@@ -729,13 +729,10 @@ static int choose_key_symbols(u64 n, int b, double entropy_bits, int max_key_bit
     double kk = std::ceil(need / entropy_bits);
     int k = kk > (double)kmax ? kmax : (int)kk;
     if (k < 1) k = 1;
-    // round the key to whole digit passes: extra symbols are free inside a pass -- but a key that overshoots a pass
-    // boundary by a bit or two is cut back instead (the "+ 10" above is margin; a sixth LSD pass over 1.9e9 pairs is 16 ms)
+    // round the key up to whole digit passes: extra symbols are free inside a pass.  (Cutting a key that overshoots a pass
+    // boundary by a bit or two back instead saves config 3 one of six LSD passes, 16 ms -- and costs it 30 ms: the rounds
+    // start at h = 20 instead of 24 and every one of them keeps more suffixes active.)
     int passes = (k * b + kRadixBits - 1) / kRadixBits;
-    if (passes > 2 && k * b - (passes - 1) * kRadixBits <= 2 && ((passes - 1) * kRadixBits) / b >= 1) {
-        --passes;
-        return ((passes * kRadixBits) / b) < kmax ? (passes * kRadixBits) / b : kmax;
-    }
     int k2 = (passes * kRadixBits) / b;
     if (k2 > kmax) k2 = kmax;
     return k2 > k ? k2 : k;
