@@ -729,8 +729,13 @@ hist16_kernel(const u64 *__restrict__ words, u64 n, u32 *__restrict__ hist, u32 
         __syncthreads();
         const u64 p_lo = n - e1, p_hi = n - 1 - e0;                // positions of the chunk, inclusive
         const u64 w_first = (p_lo * B) >> 6, w_last = (p_hi * B) >> 6;
+        // (the loads of the next step are issued before this step's shared atomics: one CTA per SM and a dependent
+        // load per step left the kernel waiting on memory -- long scoreboard 10 per issue, 1.1 TB/s)
+        u64 nhi = 0, nlw = 0;
+        if (w_first + tid <= w_last) { nhi = words[w_first + tid]; nlw = words[w_first + tid + 1]; }
         for (u64 w = w_first + tid; w <= w_last; w += kHist16Threads) {
-            const u64 hi = words[w], lw = words[w + 1];
+            const u64 hi = nhi, lw = nlw;
+            if (w + kHist16Threads <= w_last) { nhi = words[w + kHist16Threads]; nlw = words[w + kHist16Threads + 1]; }
             const u64 q0 = w * PER;
             if (q0 >= p_lo && q0 + (PER - 1) <= p_hi) {
 #pragma unroll

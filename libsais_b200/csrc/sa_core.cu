@@ -375,34 +375,52 @@ rank_flags_kernel(const RankArgs a)
 // Round 0 of the fused MSD path: bucket_sort_kernel (partition.cuh, BucketFuse) left one flag byte per slot (bit 0 head,
 // bit 1 active).  Packs them into rank_flags' mask bytes (heads | actives << 4 per 4 slots) and takes the per-warp and
 // per-tile aggregates: slot of the last head, active suffixes, active groups.
+static const int kAggTiles = 8;          // tiles per CTA of rank_agg_kernel (one tile per CTA: 262 144 CTAs for 2^28 slots, 1.26 TB/s)
 __global__ void __launch_bounds__(kRankThreads)
 rank_agg_kernel(const u8 *__restrict__ flags, u32 *__restrict__ masks, u64 N, u32 *__restrict__ wagg, u32 *__restrict__ tagg, u64 ntiles)
 {
-    __shared__ u32 s_wagg[3][kRankWarps];
+    __shared__ u32 s_wagg[kAggTiles][3][kRankWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u64 tile = blockIdx.x;
-    const u64 j0 = tile * kRankTile + (u64)tid * 4;
-    u32 f4 = 0;
-    if (j0 + 4 <= N && ((uintptr_t)flags & 3) == 0) f4 = *reinterpret_cast<const u32 *>(flags + j0);
-    else { for (int i = 0; i < 4; ++i) if (j0 + i < N) f4 |= (u32)flags[j0 + i] << (8 * i); }
-    const u32 h = (f4 & 1u) | ((f4 >> 7) & 2u) | ((f4 >> 14) & 4u) | ((f4 >> 21) & 8u);
-    const u32 am = ((f4 >> 1) & 1u) | ((f4 >> 8) & 2u) | ((f4 >> 15) & 4u) | ((f4 >> 22) & 8u);
-    const u32 gm = am & h;
-    if (j0 < N) reinterpret_cast<u8 *>(masks)[j0 >> 2] = (u8)(h | (am << 4));
-    const u32 w_head = __reduce_max_sync(0xffffffffu, h ? (u32)j0 + (u32)(31 - __clz(h)) : 0u);
-    const u32 w_act = __reduce_add_sync(0xffffffffu, (u32)__popc(am));
-    const u32 w_grp = __reduce_add_sync(0xffffffffu, (u32)__popc(gm));
-    if (lane == 0) {
-        u32 *wa = wagg + (tile * kRankWarps + warp) * 3;
-        wa[0] = w_head; wa[1] = w_act; wa[2] = w_grp;
-        s_wagg[0][warp] = w_head; s_wagg[1][warp] = w_act; s_wagg[2][warp] = w_grp;
+    const u64 tile0 = (u64)blockIdx.x * kAggTiles;
+    const bool vec = ((uintptr_t)flags & 3) == 0;
+    u32 f4[kAggTiles];
+#pragma unroll
+    for (int t = 0; t < kAggTiles; ++t) {                  // all loads first
+        const u64 j0 = (tile0 + t) * kRankTile + (u64)tid * 4;
+        f4[t] = 0;
+        if (tile0 + t < ntiles) {
+            if (vec && j0 + 4 <= N) f4[t] = *reinterpret_cast<const u32 *>(flags + j0);
+            else { for (int i = 0; i < 4; ++i) if (j0 + i < N) f4[t] |= (u32)flags[j0 + i] << (8 * i); }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kAggTiles; ++t) {
+        const u64 tile = tile0 + t;
+        if (tile >= ntiles) break;                         // uniform
+        const u64 j0 = tile * kRankTile + (u64)tid * 4;
+        const u32 f = f4[t];
+        const u32 h = (f & 1u) | ((f >> 7) & 2u) | ((f >> 14) & 4u) | ((f >> 21) & 8u);
+        const u32 am = ((f >> 1) & 1u) | ((f >> 8) & 2u) | ((f >> 15) & 4u) | ((f >> 22) & 8u);
+        const u32 gm = am & h;
+        if (j0 < N) reinterpret_cast<u8 *>(masks)[j0 >> 2] = (u8)(h | (am << 4));
+        const u32 w_head = __reduce_max_sync(0xffffffffu, h ? (u32)j0 + (u32)(31 - __clz(h)) : 0u);
+        const u32 w_act = __reduce_add_sync(0xffffffffu, (u32)__popc(am));
+        const u32 w_grp = __reduce_add_sync(0xffffffffu, (u32)__popc(gm));
+        if (lane == 0) {
+            u32 *wa = wagg + (tile * kRankWarps + warp) * 3;
+            wa[0] = w_head; wa[1] = w_act; wa[2] = w_grp;
+            s_wagg[t][0][warp] = w_head; s_wagg[t][1][warp] = w_act; s_wagg[t][2][warp] = w_grp;
+        }
     }
     __syncthreads();
-    if (tid < 3) {
-        u32 r = 0;
+    if (tid < 3 * kAggTiles) {
+        const int t = tid / 3, q = tid % 3;
+        if (tile0 + t < ntiles) {
+            u32 r = 0;
 #pragma unroll
-        for (int w = 0; w < kRankWarps; ++w) { u32 v = s_wagg[tid][w]; r = tid == 0 ? (v > r ? v : r) : r + v; }
-        tagg[(u64)tid * ntiles + tile] = r;
+            for (int w = 0; w < kRankWarps; ++w) { u32 v = s_wagg[t][q][w]; r = q == 0 ? (v > r ? v : r) : r + v; }
+            tagg[(u64)q * ntiles + tile0 + t] = r;
+        }
     }
 }
 
@@ -1011,7 +1029,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     ra.masks = rmasks; ra.wagg = rwagg; ra.tagg = rtagg; ra.nchunks = ceil_div(n, 32);
     ra.ntiles = rank_tiles; ra.out_counts = c.d_scalars + S_NACT;
     ra.pair_idx = nullptr; ra.pair_val = nullptr; ra.phist = nullptr; ra.pshift = 0;
-    if (msd_fused) LSC_LAUNCH(c, KC_RANK_INIT, (double)n * 1.25, rank_agg_kernel, (u32)rank_tiles, kRankThreads, 0, (const u8 *)a_slot1, rmasks, n, rwagg, rtagg, rank_tiles);
+    if (msd_fused) LSC_LAUNCH(c, KC_RANK_INIT, (double)n * 1.25, rank_agg_kernel, (u32)ceil_div(rank_tiles, (u64)kAggTiles), kRankThreads, 0, (const u8 *)a_slot1, rmasks, n, rwagg, rtagg, rank_tiles);
     else LSC_LAUNCH(c, KC_RANK_INIT, (double)n * (12 + (SA ? 4 : 0) + (bwt_mode ? 1 : 0)), rank_flags_kernel<true>, (u32)rank_tiles, kRankThreads, 0, ra);
     LSC_LAUNCH(c, KC_RANK_SCAN, (double)rank_tiles * 24, rank_scan_kernel, kRankScanCtas, 1024, 0, rtagg, rank_tiles, c.d_scalars + S_NACT);
     if (!read_round_scalars(c)) return -2;
