@@ -13,16 +13,18 @@
 //
 // po_round_kernel, one tile = the groups that start in a window of the list (whole groups, <= kPoCap elements):
 //   gather  r = ISA[p + h] + 1
-//   order   every element counts the members of its group that precede it (key (r, index): unique); a thread owns
-//           8 consecutive elements and shares each shared-memory load between them
+//   order   runs of neighbours with the same r keep their relative order, so only the head of a run is ordered by counting
+//           the members of its group in front of it (ties included) and behind it (smaller only), 8 lanes per head; tiles
+//           with many runs order every element, a thread taking 8 consecutive members of ONE group and sharing each
+//           shared-memory load between them (one integer-pipe compare + one FMA-pipe predicated add per pair)
 //   rank    new sub-group heads by neighbour compare in sorted order; new rank = old rank + offset of the head
 //   emit    final suffixes (sub-group of one): SA[slot], BWT row, primary index, aux sample -- each written once,
-//           when it is known; changed ranks as (position, rank) pairs at the element's list index (applied to ISA
-//           by po_apply_kernel AFTER the round: a round must read the ranks of the round before); the suffixes
-//           that stay active, compacted in list order through a chained scan over the tiles (atomic tickets,
-//           decoupled look-back on one status word per tile)
+//           when it is known; changed ranks as (position, rank) pairs, grouped by text neighbourhood and staged through
+//           shared memory (applied to ISA by po_apply_kernel AFTER the round: a round must read the ranks of the round
+//           before); the suffixes that stay active, compacted in list order through a chained scan over the tiles (atomic
+//           tickets, warp-wide decoupled look-back on one status word per tile)
 // Replaces local_count / local_sort + rank_flags + rank_scan + rank_apply + the partition pass and scatter of the
-// ISA update: ~50 instead of ~300 bytes of traffic per active suffix and round.
+// ISA update: 28 instead of ~300 bytes of DRAM traffic per active suffix and round (profiles/po_rounds_r2.md).
 // (Reference counterpart: none -- libsais is SA-IS, src/libsais.c:2157-4101; this is the B200-native SA core.)
 #pragma once
 #include "radix_sort.cuh"
@@ -37,8 +39,7 @@ static const u32 kPoNone = 0xFFFFFFFFu;          // pair slot without an update
 static const u32 kPoMaxGroup = 1024;             // larger groups after round 0: the slot-ordered path of round 1 handles the text
 
 struct PoArgs {
-    const u64 *kv_keys; const u32 *kv_vals;      // first round: rank = low word of kv_keys[j], position = kv_vals[j] (output of the group sort)
-    const u32 *a_pos, *a_rank;                   // later rounds
+    const u32 *a_pos, *a_rank;                   // the active list: position, rank of the suffix's group
     u64 N, n, h; u32 C;                          // list length, text length, sorted prefix length, window of a tile
     int bin_shift;                               // rank updates of a tile are grouped by (position >> bin_shift) & 255
     u32 ntiles;                                  // tiles of the round (= CTAs)
@@ -49,12 +50,6 @@ struct PoArgs {
     u64 *status; u32 *ticket; u64 *out_counts;   // chained scan; out_counts[0] = active suffixes, [1] = active groups after the round
     u32 *err;
 };
-
-template <bool KV> __device__ __forceinline__ u32 po_rank_at(const PoArgs &a, u64 j)
-{
-    return KV ? reinterpret_cast<const u32 *>(a.kv_keys)[2 * j] : a.a_rank[j];
-}
-template <bool KV> __device__ __forceinline__ u32 po_pos_at(const PoArgs &a, u64 j) { return KV ? a.kv_vals[j] : a.a_pos[j]; }
 
 // exclusive max-scan and sum-scan over the threads of the CTA (two barriers)
 __device__ __forceinline__ void po_block_scan(u32 mymax, u32 mysum, u32 &exmax, u32 &exsum, u32 &total, u32 (*s_scan)[kPoWarps], int lane, int warp)
@@ -118,7 +113,6 @@ __device__ __forceinline__ void po_block_scan3(u32 max1, u32 max2, u32 mysum, u3
     __syncthreads();
 }
 
-template <bool KV>
 __global__ void __launch_bounds__(kPoThreads, 4)
 po_round_kernel(const PoArgs a)
 {
@@ -152,7 +146,7 @@ po_round_kernel(const PoArgs a)
         bool found = false;
         for (u32 off = 0; !found; off += kPoThreads) {
             const u64 j = target + off + tid;
-            const bool hd = j < N ? (j == 0 || po_rank_at<KV>(a, j) != po_rank_at<KV>(a, j - 1)) : j == N;
+            const bool hd = j < N ? (j == 0 || a.a_rank[j] != a.a_rank[j - 1]) : j == N;
             if (hd) atomicMin(&bounds[which], (u32)(j - t0));
             found = __syncthreads_or(hd) != 0;
             if (!found && off > (u32)kPoCap) { ok = false; found = true; }
@@ -174,8 +168,8 @@ po_round_kernel(const PoArgs a)
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
                 const u32 idx = i * kPoThreads + tid;
-                p[i] = idx < cnt ? po_pos_at<KV>(a, s + idx) : 0;
-                rk[i] = idx < cnt ? po_rank_at<KV>(a, s + idx) : 0;
+                p[i] = idx < cnt ? a.a_pos[s + idx] : 0;
+                rk[i] = idx < cnt ? a.a_rank[s + idx] : 0;
             }
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {

@@ -1106,9 +1106,13 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     }
     // ---- position-ordered rounds (po_rounds.cuh): no group larger than kPoMaxGroup and enough suffixes left to pay for
     // the one-time reordering of the groups.  From here on the active record is (position, rank of the group).
+    // The test is repeated before every slot-ordered round: a text whose round-0 groups are too large (natural language: the
+    // suffixes of a frequent word) runs slot-ordered rounds until they have split far enough, then switches over.
     int po_env = 1;
     { const char *env = getenv("LIBSAIS_CUDA_PO"); if (env && *env) po_env = atoi(env); }
-    if (po_env && local_on && N >= kLocalMin && !(c.h_scalars[S_BIGGRP] & 4)) {
+    bool flags_valid = local_on && N >= kLocalMin;              // S_BIGGRP describes the current active list
+    while (N > 0) {
+    if (po_env && local_on && flags_valid && N >= kLocalMin && !(c.h_scalars[S_BIGGRP] & 4)) {
         const u64 f = c.h_scalars[S_BIGGRP];
         const u32 limit = !(f & 1) ? kLocalCountLimit : !(f & 2) ? 512u : kPoMaxGroup;
         const u32 C = (u32)kPoCap - limit;
@@ -1146,14 +1150,14 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             c.check(cudaMemsetAsync(sort_temp, 0, tiles * sizeof(u64), st));
             c.check(cudaMemsetAsync(c.d_scalars + S_TICKET, 0, sizeof(u64), st));
             c.check(cudaMemsetAsync(c.d_scalars + S_NACT, 0, 2 * sizeof(u64), st));
-            PoArgs pa; pa.kv_keys = nullptr; pa.kv_vals = nullptr; pa.a_pos = lp[cur ^ 1]; pa.a_rank = lr[cur ^ 1];
+            PoArgs pa; pa.a_pos = lp[cur ^ 1]; pa.a_rank = lr[cur ^ 1];
             pa.N = N; pa.n = n; pa.h = h; pa.C = C; pa.bin_shift = bin_shift; pa.ISA = ISA; pa.o_pos = lp[cur]; pa.o_rank = lr[cur];
             pa.pair_pos = pair_pos; pa.pair_rank = pair_rank;                        // both 16-byte aligned (po_apply_kernel)
             pa.SA = SA; pa.rows = bwt_mode ? opt.bwt_rows : nullptr; pa.text = bwt_mode ? (const u8 *)d_T : nullptr;
             pa.aux_mask = ra.aux_mask; pa.aux_shift = ra.aux_shift; pa.aux_I = opt.aux_I; pa.primary = c.d_scalars + S_PRIMARY;
             pa.status = (u64 *)sort_temp; pa.ticket = (u32 *)(c.d_scalars + S_TICKET); pa.out_counts = c.d_scalars + S_NACT; pa.err = err;
             pa.ntiles = (u32)tiles;
-            LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (8 + 4 + 8 + 8), po_round_kernel<false>, (u32)tiles, kPoThreads, 0, pa);
+            LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (8 + 4 + 8 + 8), po_round_kernel, (u32)tiles, kPoThreads, 0, pa);
             LSC_LAUNCH(c, KC_SCATTER, (double)N * 12, po_apply_kernel, (u32)ceil_div(N, 2048), 256, 0, pa.pair_pos, pa.pair_rank, N, ISA);
             if (!read_round_scalars(c)) return -2;
             N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
@@ -1161,8 +1165,9 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             c.rounds.push_back(r);
             first = false; cur ^= 1; h *= 2; ++round;
         }
+        break;
     }
-    while (N > 0) {
+    {
         if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
         const int grp_bits = bits_for(G > 1 ? G - 1 : 1);
         RoundStat r; r.h = h; r.n_active = N; r.key_bits = rank_bits + grp_bits; r.passes = 0; r.n_groups = 0;
@@ -1206,11 +1211,13 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         if (!read_round_scalars(c)) return -2;
         N = c.h_scalars[S_NACT]; G = c.h_scalars[S_NGRP];
         win = checked ? local_window() : 0;
+        flags_valid = checked;
         r.n_groups = G;
         c.rounds.push_back(r);
         u32 *t = slot_cur; slot_cur = slot_nxt; slot_nxt = t;
         h *= 2;
         ++round;
+    }
     }
     out->SA = SA; out->ISA = ISA; out->isa_complete = !lazy;
     out->primary = c.h_scalars[S_PRIMARY];

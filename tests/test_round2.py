@@ -247,6 +247,10 @@ def test_position_ordered_rounds(cu):
              "exact_repeats": np.tile(gen.dna(5, 30_000), 9), "tail_repeat": np.concatenate([gen.dna(6, 100_000), gen.dna(6, 100_000)[:70_000]]),
              "bytes_copies": np.tile(gen.rand_bytes(4, 50_000), 4), "runs": np.repeat(gen.dna(8, 40_000), 5),
              "small": gen.repetitive_dna(300, 20), "binary": (rng.integers(0, 2, 300_000) + 48).astype(np.uint8)}
+    # groups of 3000 after round 0 (a 40-symbol motif) that split into groups of ~300 (ten 300-symbol continuations): slot-ordered
+    # rounds first, the switch to the position-ordered rounds once no group exceeds 1024
+    motif, conts = gen.dna(21, 40), [gen.dna(30 + i, 300) for i in range(10)]
+    texts["late_switch"] = np.concatenate([np.concatenate([motif, conts[int(rng.integers(0, 10))], gen.dna(100 + i, int(rng.integers(5, 60)))]) for i in range(3000)])
     texts["mutated_bytes"] = texts["bytes_copies"].copy()
     texts["mutated_bytes"][rng.integers(0, len(texts["mutated_bytes"]), 300)] = 7
     knobs = ("LIBSAIS_CUDA_PO", "LIBSAIS_CUDA_LOCAL_MIN", "LIBSAIS_CUDA_PO_BIN")
