@@ -379,6 +379,8 @@ def run_c3(ctx, dev, peak):
     kern, tot_bytes, worst = kernel_tables(agg, 1, ms, peak)
     out["sa"] = {"rc": rc, "ms": round(ms, 2), "mbs": round(n / 1e6 / (ms / 1e3), 1), "launches": st["total_launches"],
                  "rounds": [(r["h"], r["n_active"], r["passes"]) for r in st["rounds"]],
+                 "per_round": [{"h": r["h"], "n_active": r["n_active"], "ms": round(r["ms"], 2), "bytes_moved": r["bytes"],
+                                "frac_of_peak": round(r["bytes"] / max(r["ms"], 1e-9) / 1e6 / peak, 4)} for r in st["rounds"]],
                  "bytes_moved": tot_bytes, "moved_bytes_frac_of_peak": round(tot_bytes / (ms / 1e3) / 1e9 / peak, 4),
                  "kernels": {k: v for k, v in kern.items() if v["share_of_step"] >= 0.01}}
     out["sa"]["verify"] = check.verify_sa(dT, dSA, n)

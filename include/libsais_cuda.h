@@ -34,6 +34,8 @@ typedef struct libsais_cuda_round {
     uint64_t n_groups;   /* unresolved groups left after the round */
     int32_t  passes;     /* radix digit passes */
     int32_t  key_bits;   /* key bits sorted */
+    double   device_ms;  /* with profiling on: device time of the round's kernels (CUDA events) ... */
+    double   bytes;      /* ... and the algorithmic bytes they moved */
 } libsais_cuda_round;
 
 /* Number of CUDA devices visible (0 when there is no usable GPU). */

@@ -27,7 +27,7 @@ class Stats(C.Structure):
 
 class Round(C.Structure):
     _fields_ = [("h", C.c_uint64), ("n_active", C.c_uint64), ("n_groups", C.c_uint64),
-                ("passes", C.c_int32), ("key_bits", C.c_int32)]
+                ("passes", C.c_int32), ("key_bits", C.c_int32), ("device_ms", C.c_double), ("bytes", C.c_double)]
 
 
 def load_library(build_if_missing=True):
@@ -116,7 +116,7 @@ class Context:
             rd = Round()
             self.lib.libsais_cuda_get_round(self.handle, r, C.byref(rd))
             rounds.append({"h": int(rd.h), "n_active": int(rd.n_active), "n_groups": int(rd.n_groups),
-                           "passes": int(rd.passes), "key_bits": int(rd.key_bits)})
+                           "passes": int(rd.passes), "key_bits": int(rd.key_bits), "ms": float(rd.device_ms), "bytes": float(rd.bytes)})
         return {"total_launches": int(s.total_launches), "device_ms": float(s.device_ms),
                 "workspace_bytes": int(s.workspace_bytes), "kernels": per, "rounds": rounds}
 

@@ -700,6 +700,7 @@ int32_t libsais_cuda_get_round(const void *ctx, int32_t round, libsais_cuda_roun
     if (!c || !out || round < 0 || (size_t)round >= c->rounds.size()) return -1;
     const RoundStat &r = c->rounds[round];
     out->h = r.h; out->n_active = r.n_active; out->n_groups = r.n_groups; out->passes = r.passes; out->key_bits = r.key_bits;
+    out->device_ms = r.ms; out->bytes = r.bytes;
     return 0;
 }
 // Give the context's device workspace and pinned staging back to the system (it is re-grown on the next call).

@@ -85,7 +85,7 @@ void Ctx::begin(int kc, double algo_bytes)
     launches[kc]++; total_launches++;
     bytes[kc] += algo_bytes;
     if (!profiling) return;
-    Pending p; p.kc = kc; p.bytes = algo_bytes;
+    Pending p; p.kc = kc; p.bytes = algo_bytes; p.round = (int)rounds.size();      // the round being built (its stat is pushed when it ends)
     cudaEvent_t ev[2];
     for (int i = 0; i < 2; ++i) {
         if (!event_pool.empty()) { ev[i] = event_pool.back(); event_pool.pop_back(); }
@@ -106,7 +106,10 @@ void Ctx::resolve_profile()
 {
     for (auto &p : pending) {
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) ms[p.kc] += t; else cudaGetLastError();
+        if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) {
+            ms[p.kc] += t;
+            if (p.round >= 0 && (size_t)p.round < rounds.size()) { rounds[p.round].ms += t; rounds[p.round].bytes += p.bytes; }
+        } else cudaGetLastError();
         event_pool.push_back(p.a); event_pool.push_back(p.b);
     }
     pending.clear();

@@ -14,6 +14,8 @@ struct RoundStat {
     u64 n_groups;   // non-singleton groups they formed
     int passes;     // radix digit passes executed
     int key_bits;   // significant key bits sorted
+    double ms = 0;      // with profiling: device time of the kernels launched in the round (CUDA events)
+    double bytes = 0;   //                 and their algorithmic bytes
 };
 
 struct Ctx {
@@ -37,7 +39,7 @@ struct Ctx {
     // launch accounting
     bool profiling = false;
     int pass_class_override = -1;         // account onesweep launches to another kernel class (partitioned scatter)
-    struct Pending { int kc; cudaEvent_t a, b; double bytes; };
+    struct Pending { int kc; cudaEvent_t a, b; double bytes; int round; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;
     u64 launches[KC_COUNT] = {0};

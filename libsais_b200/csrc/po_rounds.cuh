@@ -130,6 +130,8 @@ po_round_kernel(const PoArgs a)
     __shared__ u64 s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // Four CTAs per SM (64 registers, 47.7 KB).  Five -- positions re-read from the list instead of kept in shared memory,
+    // 48 registers with a few spills -- were slower: 268 -> 282 ms over the rounds of config 3.
     // One tile per CTA.  (A persistent variant -- CTAs drawing tickets until they run out, so that a tile's stores drain under
     // the next tile's gather instead of on EXIT, where a fifth of the warp samples sit -- was slower: 58 -> 63 ms per round.)
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
