@@ -296,6 +296,7 @@ IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *f
     // A pinned output buffer receives the rows of settled slots while round 0 still sorts (boundary
     // src/libsais.c:7097-7121): the device alias of U is needed for the few rows that are sent again at the end.
     u8 *U_dev_alias = nullptr;
+    const uint8_t last_symbol = T[n - 1];                 // U may be T (include/libsais.h): read before any row lands in U
     if (host_is_pinned(U) && cudaHostGetDevicePointer((void **)&U_dev_alias, (void *)U, 0) == cudaSuccess && U_dev_alias) { opt.h_U = U; opt.h_T = T; }
     else cudaGetLastError();
     if (build_sa(*c, d_T, 1, (u64)n, opt, &res) != 0) return -2;
@@ -310,7 +311,7 @@ IDX bwt_body(Ctx *c, const uint8_t *T, uint8_t *U, IDX *A, IDX n, IDX fs, IDX *f
         if (p0 + 1 < res.p0_hi) c->check(cudaMemcpyAsync(U + p0 + 1, d_rows + p0 + 1, res.p0_hi - p0 - 1, cudaMemcpyDeviceToHost, c->stream));
         if (run_bwt_patch(*c, res.patch_slots, res.n_patch, d_rows, U_dev_alias, p0) != 0) return -2;
         call.stop_timer();
-        U[0] = T[n - 1];
+        U[0] = last_symbol;
     } else {
         if (opt.h_U && c->copy_stream) c->check(cudaStreamSynchronize(c->copy_stream));       // chunks may be in flight into U: let them land first
         if (run_bwt_finish(*c, d_T, d_rows, d_U, (u64)n, res.primary) != 0) return -2;

@@ -19,6 +19,7 @@
 // (sa_core.cu) picks the kernel and the window, or falls back to the global sort.
 #pragma once
 #include "radix_sort.cuh"
+#include "lazy_rank.cuh"
 
 namespace lsc {
 
@@ -91,9 +92,11 @@ __device__ __forceinline__ bool find_tile(const u32 *__restrict__ a_grp, u64 N, 
     return ok && bounds[1] >= bounds[0] && bounds[1] - bounds[0] <= cap;
 }
 
+// LAZY: the lazy ISA -- an invalid entry is a round-0 singleton whose rank is recomputed (lazy_rank.cuh)
+template <bool LAZY>
 __global__ void __launch_bounds__(kCountThreads, 5)
 local_count_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp, const u32 *__restrict__ ISA,
-                   u64 N, u64 n, u64 h, int rank_bits, u64 *__restrict__ keys_out, u32 *__restrict__ pos_out, u32 *err)
+                   u64 N, u64 n, u64 h, int rank_bits, u64 *__restrict__ keys_out, u32 *__restrict__ pos_out, u32 *err, const LazyArgs la)
 {
     __shared__ u64 comp[kCountCap];        // ((group in tile << rank_bits | rank) << 11) | index: unique, ties by index
     __shared__ u32 vals[kCountCap];
@@ -122,6 +125,7 @@ local_count_kernel(const u32 *__restrict__ a_pos, const u32 *__restrict__ a_grp,
             const u32 idx = i * kCountThreads + tid;
             const u64 q = (u64)p[i] + h;
             r[i] = (idx < cnt && q < n) ? ISA[q] + 1 : 0;
+            if (LAZY && idx < cnt && q < n && r[i] == 0) r[i] = lazy_rank(la, q) + 1;          // kIsaInvalid + 1 == 0
         }
 #pragma unroll
         for (int i = 0; i < kCountIPT; ++i) {

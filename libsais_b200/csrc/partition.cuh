@@ -965,6 +965,7 @@ struct BucketFuse {
     int on;
     u8 *flags; u8 *rows; u64 tail_start;        // flags[slot]: bit 0 head, bit 1 active (rank_agg_kernel packs them into the mask bytes)
     u64 aux_mask; int aux_shift; u32 *aux_I; u64 *primary;
+    u64 *big_flag;          // bit 0 is set when some group has more than 128 members (sa_core.cu: the lazy rounds then sort globally)
 };
 
 // key of element idx of the partitioned array.  in32: the array holds only the key bits below the 16-bit bucket
@@ -1099,6 +1100,7 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
             const u64 o = s + beg + r;
             vout[o] = p;
             fz.flags[o] = (u8)((head ? 1u : 0u) | (active ? 2u : 0u));
+            if (same > 128u && head) atomicOr((unsigned long long *)fz.big_flag, 1ull);
             if (fz.rows) fz.rows[o] = prevb[i];
             if (!active) {
                 if (p == 0) *fz.primary = o + 1;
@@ -1145,6 +1147,7 @@ bucket_sort_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin, con
         const bool tail = (u64)p >= fz.tail_start;
         const bool head = tail || before == 0, active = !tail && same > 1;
         fz.flags[o] = (u8)((head ? 1u : 0u) | (active ? 2u : 0u));
+        if (same > 128u && head) atomicOr((unsigned long long *)fz.big_flag, 1ull);
         if (fz.rows) fz.rows[o] = (u8)(key & lowmask);
         if (!active) {
             if (p == 0) *fz.primary = o + 1;

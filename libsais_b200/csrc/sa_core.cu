@@ -27,6 +27,7 @@
 #include "core.h"
 #include "radix_sort.cuh"
 #include "scatter.cuh"
+#include "lazy_rank.cuh"
 #include "local_sort.cuh"
 #include "partition.cuh"
 #include "po_rounds.cuh"
@@ -150,16 +151,6 @@ pack_bytes_kernel(const u8 *__restrict__ T, u64 n, u64 *__restrict__ words, u64 
     words[j] = w;
 }
 
-// k-mer of suffix p: the K most significant bits of the 64-bit window at bit p*b
-__device__ __forceinline__ u64 kmer_at(const u64 *__restrict__ words, u64 p, int b, int K)
-{
-    u64 bit = p * (u64)b;
-    u64 q = bit >> 6; int off = (int)(bit & 63);
-    u64 hi = words[q], lo = words[q + 1];
-    u64 x = off ? ((hi << off) | (lo >> (64 - off))) : hi;
-    return x >> (64 - K);
-}
-
 // Round-0 element generator: element i <-> position p = n-1-i (descending positions: see the
 // end-of-text rule above), key = k-mer of suffix p (<< key_shift, | preceding byte in BWT mode),
 // value = p.  Evaluated by the histogram kernel and by the first digit pass, so the initial
@@ -211,7 +202,6 @@ static const int kRankThreads = 256;
 static const int kRankIPT = 4;
 static const int kRankTile = kRankThreads * kRankIPT;
 static const int kRankWarps = kRankThreads / 32;
-static const u32 kIsaInvalid = 0xFFFFFFFFu;
 __device__ __forceinline__ u64 ceil_div_dev(u64 a, u64 b) { return (a + b - 1) / b; }
 
 struct RankArgs {
@@ -571,26 +561,6 @@ rank_apply_kernel(const RankArgs a)
     }
 }
 
-// Lazy ISA: rank of a round-0 singleton q, recomputed from the sorted round-0 keys (s0_keys == nullptr: from the
-// k-mers of the suffixes in slot order -- the fused MSD path never writes the sorted keys; later rounds only
-// permute positions inside groups of equal k-mers, so the suffix array in progress serves as s0_pos).
-struct LazyArgs { const u64 *words; int b; int K; const u64 *s0_keys; const u32 *s0_pos; int key_shift; u64 tail_start; u64 n; };
-
-__device__ __forceinline__ u32 lazy_rank(const LazyArgs &la, u64 q)
-{
-    const u64 kq = kmer_at(la.words, q, la.b, la.K);
-    u64 lo = 0, hi = la.n;                               // lower bound of kq among the sorted k-mers
-    while (lo < hi) {
-        u64 mid = (lo + hi) >> 1;
-        const u64 km = la.s0_keys ? la.s0_keys[mid] >> la.key_shift : kmer_at(la.words, (u64)la.s0_pos[mid], la.b, la.K);
-        if (km < kq) lo = mid + 1; else hi = mid;
-    }
-    u64 s = lo;
-    if (q >= la.tail_start) { while (s + 1 < la.n && (u64)la.s0_pos[s] != q) ++s; }       // its own slot
-    else { while (s + 1 < la.n && (u64)la.s0_pos[s] >= la.tail_start) ++s; }              // first full-length suffix
-    return (u32)s;
-}
-
 // round >= 1 keys: (dense group id, rank of the suffix h positions further + 1).  The ISA gather
 // leaves the issue slots idle, so the digit histograms of the sort that follows are taken here,
 // while the keys are in registers (hist[pass][256], zeroed by the caller): the sort needs no
@@ -945,7 +915,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         BucketFuse fz; fz.on = msd_fused ? 1 : 0; fz.flags = (u8 *)a_slot1; fz.rows = bwt_mode ? opt.bwt_rows : nullptr;      // a_slot1 is idle until the second round
         fz.tail_start = n >= (u64)k ? n - (u64)k + 1 : 0;
         fz.aux_I = opt.aux_I; fz.aux_mask = opt.aux_I ? opt.aux_r - 1 : 0; fz.aux_shift = opt.aux_I ? bits_for(opt.aux_r) - 1 : 0;
-        fz.primary = c.d_scalars + S_PRIMARY;
+        fz.primary = c.d_scalars + S_PRIMARY; fz.big_flag = c.d_scalars + S_BIGGRP;
         {
             const double ab = (double)n * ((k32 ? 8.0 : 12.0) + (msd_fused ? 4.0 + (bwt_mode ? 1.0 : 0.0) + 1.0 : 12.0));
             u32 *vout = (msd_fused && SA) ? SA : valA;
@@ -1036,6 +1006,10 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
     rs.n_groups = G;
     c.rounds.push_back(rs);
+    // fused MSD path: the bucket sort saw every group's size -- when none exceeds 128 the lazy rounds order the groups where
+    // they lie (local_count_kernel<LAZY>: one kernel instead of key build + histogram + six digit passes over a few thousand pairs)
+    bool lazy_local = msd_fused && !(c.h_scalars[S_BIGGRP] & 1);
+    { const char *env = getenv("LIBSAIS_CUDA_LAZY_LOCAL"); if (env && *env && atoi(env) == 0) lazy_local = false; }
 
     // ---- lazy ISA: with few active suffixes the ranks of round-0 singletons are never scattered;
     // the rare look-ups that hit one recompute it by binary search in the sorted round-0 keys.
@@ -1071,7 +1045,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         }
     }
     LazyArgs la; la.words = words; la.b = b; la.K = K; la.s0_keys = msd_fused ? nullptr : ks; la.s0_pos = vs; la.key_shift = key_shift;
-    la.tail_start = tail_start; la.n = n;
+    la.tail_start = tail_start; la.n = n; la.boff16 = msd ? m_boff : nullptr;
 
     // ---- doubling rounds on the active suffixes
     const int rank_bits = bits_for(n);                 // k2 = ISA+1 <= n
@@ -1171,11 +1145,13 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         if (round > 80) { c.last_error = cudaErrorUnknown; return -2; }
         const int grp_bits = bits_for(G > 1 ? G - 1 : 1);
         RoundStat r; r.h = h; r.n_active = N; r.key_bits = rank_bits + grp_bits; r.passes = 0; r.n_groups = 0;
-        const bool local = local_on && win != 0 && N >= kLocalMin;
+        const bool local = (local_on && win != 0 && N >= kLocalMin) || (lazy && lazy_local);
         if (local) {
             // key build + sort in one kernel, in place of round_keys + onesweep (r.passes stays 0)
-            if (win == 1) LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_count_kernel, (u32)ceil_div(N, kCountWindow), kCountThreads, 0,
-                                     a_pos, a_grp, ISA, N, n, h, rank_bits, rk1, rv1, err);
+            if (lazy) LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_count_kernel<true>, (u32)ceil_div(N, kCountWindow), kCountThreads, 0,
+                                 a_pos, a_grp, ISA, N, n, h, rank_bits, rk1, rv1, err, la);
+            else if (win == 1) LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_count_kernel<false>, (u32)ceil_div(N, kCountWindow), kCountThreads, 0,
+                                     a_pos, a_grp, ISA, N, n, h, rank_bits, rk1, rv1, err, la);
             else LSC_LAUNCH(c, KC_LOCAL_SORT, (double)N * (4 + 4 + 4 + 12), local_sort_kernel, (u32)ceil_div(N, win), kLocalThreads, sizeof(LocalSmem),
                             a_pos, a_grp, ISA, N, n, h, rank_bits, win, rk1, rv1, err);
             where = 1;

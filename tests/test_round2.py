@@ -311,5 +311,9 @@ def test_bwt_streamed_rows_into_pinned_buffers(cu):
                 rc = lib.libsais_bwt_aux(C.c_void_p(Tp.data_ptr()), C.c_void_p(Up.data_ptr()), C.c_void_p(Ap.data_ptr()), C.c_int32(n), C.c_int32(0), None,
                                          C.c_int32(256), C.c_void_p(Ip.data_ptr()))
                 assert rc == 0 and (Up.numpy() == Ur).all() and (Ip.numpy() == Ir).all(), (name, stream)
+                # in place: U is T (allowed by include/libsais.h)
+                Tq = torch.from_numpy(T.copy()).pin_memory()
+                rc = lib.libsais_bwt(C.c_void_p(Tq.data_ptr()), C.c_void_p(Tq.data_ptr()), C.c_void_p(Ap.data_ptr()), C.c_int32(n), C.c_int32(0), None)
+                assert rc == rb and (Tq.numpy() == Ur).all(), (name, stream, "in place")
     finally:
         os.environ.pop("LIBSAIS_CUDA_STREAM_ROWS", None)

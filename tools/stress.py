@@ -67,10 +67,11 @@ def main():
         if rng.random() < 0.5: env["LIBSAIS_CUDA_LOCAL_SORT"] = str(int(rng.integers(0, 2)))
         if rng.random() < 0.5: env["LIBSAIS_CUDA_LAZY_ISA"] = str(int(rng.integers(0, 2)))
         if rng.random() < 0.2: env["LIBSAIS_CUDA_KEY_SYMBOLS"] = str(int(rng.integers(1, 9)))
+        if rng.random() < 0.3: env["LIBSAIS_CUDA_LAZY_LOCAL"] = str(int(rng.integers(0, 2)))
         if rng.random() < 0.3: env["LIBSAIS_CUDA_PO"] = str(int(rng.integers(0, 2)))
         if rng.random() < 0.6: env["LIBSAIS_CUDA_LOCAL_MIN"] = str(int(rng.choice([1, 64, 4096])))
         if rng.random() < 0.3: env["LIBSAIS_CUDA_PO_BIN"] = str(int(rng.integers(0, 12)))
-        for k in ("LIBSAIS_CUDA_LOCAL_SORT", "LIBSAIS_CUDA_LAZY_ISA", "LIBSAIS_CUDA_KEY_SYMBOLS", "LIBSAIS_CUDA_PO", "LIBSAIS_CUDA_LOCAL_MIN", "LIBSAIS_CUDA_PO_BIN"):
+        for k in ("LIBSAIS_CUDA_LOCAL_SORT", "LIBSAIS_CUDA_LAZY_ISA", "LIBSAIS_CUDA_KEY_SYMBOLS", "LIBSAIS_CUDA_PO", "LIBSAIS_CUDA_LOCAL_MIN", "LIBSAIS_CUDA_PO_BIN", "LIBSAIS_CUDA_LAZY_LOCAL"):
             os.environ.pop(k, None)
         os.environ.update(env)
         what = None
