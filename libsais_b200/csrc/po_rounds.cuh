@@ -43,6 +43,7 @@ struct PoArgs {
     u64 N, n, h; u32 C;                          // list length, text length, sorted prefix length, window of a tile
     int bin_shift;                               // rank updates of a tile are grouped by (position >> bin_shift) & 255
     u32 ntiles;                                  // tiles of the round (= CTAs)
+    u32 run_div;                                 // a tile orders run heads only when runs * run_div <= elements
     const u32 *ISA;
     u32 *o_pos, *o_rank;                         // suffixes that stay active
     u32 *pair_pos, *pair_rank;                   // [N] rank updates (kPoNone: none)
@@ -229,7 +230,7 @@ po_round_kernel(const PoArgs a)
             }
         }
         __syncthreads();
-        if (nrun * 4 <= cnt) {
+        if (nrun * a.run_div <= cnt) {
             // ---- few runs: one thread per run head counts the members of its group in front of it (ties included) and
             // behind it (smaller ranks only)
             // (8 lanes share a run head and split its group between them: with one thread per head a few warps walked whole

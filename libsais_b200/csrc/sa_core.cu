@@ -1005,7 +1005,6 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
     if (!read_round_scalars(c)) return -2;
     u64 N = c.h_scalars[S_NACT], G = c.h_scalars[S_NGRP];
     rs.n_groups = G;
-    c.rounds.push_back(rs);
     // fused MSD path: the bucket sort saw every group's size -- when none exceeds 128 the lazy rounds order the groups where
     // they lie (local_count_kernel<LAZY>: one kernel instead of key build + histogram + six digit passes over a few thousand pairs)
     bool lazy_local = msd_fused && !(c.h_scalars[S_BIGGRP] & 1);
@@ -1044,6 +1043,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             ra.phist = nullptr;
         }
     }
+    c.rounds.push_back(rs);             // (here: the rank scatter above belongs to round 0 in the per-round accounting)
     LazyArgs la; la.words = words; la.b = b; la.K = K; la.s0_keys = msd_fused ? nullptr : ks; la.s0_pos = vs; la.key_shift = key_shift;
     la.tail_start = tail_start; la.n = n; la.boff16 = msd ? m_boff : nullptr;
 
@@ -1098,6 +1098,8 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
         const int pos_bits = bits_for(n - 1);
         int bin_shift = 7;
         { const char *env = getenv("LIBSAIS_CUDA_PO_BIN"); if (env && *env) { bin_shift = atoi(env); if (bin_shift < 0) bin_shift = 0; if (bin_shift > 24) bin_shift = 24; } }
+        u32 run_div = 4;
+        { const char *env = getenv("LIBSAIS_CUDA_PO_RUNS"); if (env && *env && atoi(env) > 0) run_div = (u32)atoi(env); }
         RoundStat r0; r0.h = h; r0.n_active = N; r0.n_groups = G; r0.passes = 0; r0.key_bits = pos_bits;
         c.pass_class_override = KC_ROUND_KEYS;
         where = RadixSort<u32, u32>::sort(c, ghead_pos, gid, tmpk, tmpv, G, 0, pos_bits, sort_temp, err, &r0.passes);
@@ -1125,7 +1127,7 @@ int build_sa(Ctx &c, const void *d_T, int sym_bytes, u64 n, const SAOptions &opt
             c.check(cudaMemsetAsync(c.d_scalars + S_TICKET, 0, sizeof(u64), st));
             c.check(cudaMemsetAsync(c.d_scalars + S_NACT, 0, 2 * sizeof(u64), st));
             PoArgs pa; pa.a_pos = lp[cur ^ 1]; pa.a_rank = lr[cur ^ 1];
-            pa.N = N; pa.n = n; pa.h = h; pa.C = C; pa.bin_shift = bin_shift; pa.ISA = ISA; pa.o_pos = lp[cur]; pa.o_rank = lr[cur];
+            pa.N = N; pa.n = n; pa.h = h; pa.C = C; pa.bin_shift = bin_shift; pa.run_div = run_div; pa.ISA = ISA; pa.o_pos = lp[cur]; pa.o_rank = lr[cur];
             pa.pair_pos = pair_pos; pa.pair_rank = pair_rank;                        // both 16-byte aligned (po_apply_kernel)
             pa.SA = SA; pa.rows = bwt_mode ? opt.bwt_rows : nullptr; pa.text = bwt_mode ? (const u8 *)d_T : nullptr;
             pa.aux_mask = ra.aux_mask; pa.aux_shift = ra.aux_shift; pa.aux_I = opt.aux_I; pa.primary = c.d_scalars + S_PRIMARY;
