@@ -52,7 +52,7 @@ struct PoArgs {
     u32 *err;
 };
 
-// exclusive max-scan and sum-scan over the threads of the CTA (two barriers)
+// exclusive max-scan and sum-scan over the threads of the CTA (one barrier; the scratch must not be reused before the next barrier)
 __device__ __forceinline__ void po_block_scan(u32 mymax, u32 mysum, u32 &exmax, u32 &exsum, u32 &total, u32 (*s_scan)[kPoWarps], int lane, int warp)
 {
     u32 m = mymax, s = mysum;
@@ -72,8 +72,7 @@ __device__ __forceinline__ void po_block_scan(u32 mymax, u32 mysum, u32 &exmax, 
         if (w < warp) { cm = x > cm ? x : cm; cs += y; }
         tot += y;
     }
-    exmax = em > cm ? em : cm; exsum = es + cs; total = tot;
-    __syncthreads();
+    exmax = em > cm ? em : cm; exsum = es + cs; total = tot;       // (no trailing barrier: every call of a tile has its own scratch)
 }
 
 // c += (x <= r) / (x < r), as one compare on the integer pipe and one predicated add on the FMA pipe (float counter,
@@ -111,7 +110,6 @@ __device__ __forceinline__ void po_block_scan3(u32 max1, u32 max2, u32 mysum, u3
         tot += y;
     }
     ex1 = e1 > c1 ? e1 : c1; ex2 = e2 > c2 ? e2 : c2; exsum = es + cs; total = tot;
-    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kPoThreads, 4)
@@ -125,7 +123,7 @@ po_round_kernel(const PoArgs a)
     __shared__ __align__(16) unsigned short s_src[kPoCap];  // sorted index -> list index
     __shared__ __align__(16) unsigned short s_item[kPoItems];   // work item -> first list index of its (up to) 8 elements; later s_bin
     __shared__ __align__(16) u32 s_out[kPoCap];  // rank updates of the tile, staged in bin order (positions reuse s_rk)
-    __shared__ u32 s_scan[3][kPoWarps];
+    __shared__ u32 s_scan[4][3][kPoWarps];       // scratch of the four block scans of a tile
     __shared__ u32 bounds[2];
     __shared__ u32 s_tile;
     __shared__ u64 s_base;
@@ -143,19 +141,25 @@ po_round_kernel(const PoArgs a)
 
     // ---- the tile: from the first group head at or after t0 to the first at or after t0 + C
     bool ok = true;
-    for (int which = 0; which < 2; ++which) {
-        const u64 target = t0 + (u64)which * a.C;
-        if (target >= N) { if (tid == 0) bounds[which] = (u32)(N - t0); continue; }
-        bool found = false;
-        for (u32 off = 0; !found; off += kPoThreads) {
-            const u64 j = target + off + tid;
-            const bool hd = j < N ? (j == 0 || a.a_rank[j] != a.a_rank[j - 1]) : j == N;
-            if (hd) atomicMin(&bounds[which], (u32)(j - t0));
-            found = __syncthreads_or(hd) != 0;
-            if (!found && off > (u32)kPoCap) { ok = false; found = true; }
+    {
+        // both ends in one loop: a step looks kPoThreads elements further behind each target; one barrier per step
+        const u64 tg0 = t0, tg1 = t0 + a.C;
+        if (tid == 0) { if (tg0 >= N) bounds[0] = (u32)(N - t0); if (tg1 >= N) bounds[1] = (u32)(N - t0); }
+        for (u32 off = 0;; off += kPoThreads) {
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const u64 target = which ? tg1 : tg0;
+                if (target >= N) continue;
+                const u64 j = target + off + tid;
+                const bool hd = j < N ? (j == 0 || a.a_rank[j] != a.a_rank[j - 1]) : j == N;
+                if (hd) atomicMin(&bounds[which], (u32)(j - t0));
+            }
+            __syncthreads();
+            if (bounds[0] != 0xFFFFFFFFu && bounds[1] != 0xFFFFFFFFu) break;          // uniform: shared memory after the barrier
+            if (off > (u32)kPoCap) { ok = false; break; }
+            __syncthreads();                          // (rare: a second step) everyone has read bounds[] before the next atomics
         }
     }
-    __syncthreads();
     ok = ok && bounds[1] >= bounds[0] && bounds[1] - bounds[0] <= (u32)kPoCap;
     if (!ok && tid == 0) *a.err = 2;             // a group larger than promised
     const u32 cnt = ok ? bounds[1] - bounds[0] : 0;
@@ -211,7 +215,7 @@ po_round_kernel(const PoArgs a)
                 if (rh) { rm |= 1u << i; lastrun = idx0 + i; }
             }
             u32 carry, carryrun, before;
-            po_block_scan3(last, lastrun, (u32)__popc(rm), carry, carryrun, before, nrun, s_scan, lane, warp);
+            po_block_scan3(last, lastrun, (u32)__popc(rm), carry, carryrun, before, nrun, s_scan[0], lane, warp);
             u32 cur = carry, currun = carryrun;
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
@@ -267,7 +271,7 @@ po_round_kernel(const PoArgs a)
             for (int i = 0; i < kPoIPT; ++i)
                 if ((hm >> i) & 1u) mine += ((u32)s_ge[idx0 + i] - (idx0 + i) + kPoIPT - 1) / kPoIPT;
             u32 dummy, off;
-            po_block_scan(0, mine, dummy, off, nitems, s_scan, lane, warp);
+            po_block_scan(0, mine, dummy, off, nitems, s_scan[1], lane, warp);
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
                 if ((hm >> i) & 1u) {
@@ -332,7 +336,7 @@ po_round_kernel(const PoArgs a)
                 }
             }
             u32 carry, excl;
-            po_block_scan(last, (u32)__popc(actm), carry, excl, total, s_scan, lane, warp);   // (its barriers: every gathered rank has been read)
+            po_block_scan(last, (u32)__popc(actm), carry, excl, total, s_scan[2], lane, warp);   // (its barriers: every gathered rank has been read)
             u32 cur = carry;
 #pragma unroll
             for (int i = 0; i < kPoIPT; ++i) {
@@ -363,7 +367,7 @@ po_round_kernel(const PoArgs a)
         {
             const u32 c = s_bin[tid];
             u32 dummy, ex;
-            po_block_scan(0, c, dummy, ex, nchanged, s_scan, lane, warp);
+            po_block_scan(0, c, dummy, ex, nchanged, s_scan[3], lane, warp);
             s_bin[tid] = ex;
         }
     }
