@@ -91,3 +91,18 @@ def test_product_does_not_reference_the_oracle():
                 assert "liboracle" not in text and "oracle/" not in text and "_ref" not in text, os.path.join(dp, f)
     out = subprocess.run(["ldd", os.path.join(pkg, "libsais_cuda.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out and "libsais_ref" not in out
+
+
+def test_python_mirrors_of_the_stats_structs_match_the_header(tmp_path):
+    """libsais_b200.Stats / Round are ctypes mirrors of libsais_cuda_stats / libsais_cuda_round (include/libsais_cuda.h):
+    a C99 program prints the compiler's sizes and field offsets, which must equal the mirrors'."""
+    import libsais_b200
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "libsais_cuda.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(libsais_cuda_round), offsetof(libsais_cuda_round, key_bits),\n'
+                   '    offsetof(libsais_cuda_round, device_ms), offsetof(libsais_cuda_round, bytes), sizeof(libsais_cuda_stats)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    R = libsais_b200.Round
+    assert got == [C.sizeof(R), R.key_bits.offset, R.device_ms.offset, R.bytes.offset, C.sizeof(libsais_b200.Stats)]
